@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the prototype pseudo-labelling hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl onda|reference] [--d 256|2048]
+
+One *step* = the fused pass over one batch of synthetic, Cityscapes-shaped input: hard
+pseudo-labels + soft predictions + per-class feature sum / sum of squares / count + batch
+confidence statistics, followed by the EMA prototype update -- what the reference does with
+``pseudo_labels`` x2 + ``ma`` (prototypes_hybrid_switch.py:89-93, prototypes.py:292-294).
+
+Workload (config.workload): BASELINE.json configs[2], the batch-sharded prototype path at
+1024x512 (65x129 stride-8 map), 19 classes, mahalanobis, hybrid_switch.yml parameters, with
+B=32 images PER GPU (weak scaling: every rank keeps 32 images; the only collective is the
+all-reduce of the 19x(2D+1)+8 class-sum/statistics buffer before the EMA update).
+
+Printed (rank 0, one JSON line): ``value`` = pixels/s over all ranks with inputs resident in
+HBM; ``e2e`` = the same through the public API from pinned HOST buffers (H2D of feat/prior/out
+and D2H of labels + statistics inside the timed region); ``roofline`` for the dominant kernel
+(algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json); ``cpu_baseline`` = the oracle
+port of the reference timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+C = 19
+H, W = 65, 129            # stride-8 map of a 1024x512 image (H/8+1, W/8+1)
+B_PER_GPU = 32
+PARAMS = dict(ma_lambda=0.9995, tau=1, thresh=0.3, distance_metric="mahalanobis")  # configs/hybrid_switch.yml
+METRIC = "prototype pseudo-label px/s"
+UNIT = "px/s"
+
+
+def algorithmic_bytes_per_pixel(d):
+    """feat read once + prior read + EMA-logit read + soft write + int64 label."""
+    return 4 * d + 4 * C + 4 * C + 4 * C + 8
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def gpu_inputs(torch, device, d, n_sets, seed):
+    """Synthetic Cityscapes-shaped inputs generated on the device (SURVEY.md 8d recipe)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    protos = torch.randn(C, d, generator=g, device=device) * 2.5
+    sq_mean = protos ** 2 + torch.rand(C, d, generator=g, device=device) * 1.5 + 0.5
+    counter = torch.floor(torch.rand(C, generator=g, device=device) * 6.9e4 + 1e3)
+    sets = []
+    for _ in range(n_sets):
+        lab = torch.randint(0, C, (B_PER_GPU, (H + 7) // 8, (W + 7) // 8), generator=g, device=device)
+        lab = lab.repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :H, :W]
+        feat = torch.randn(B_PER_GPU, d, H, W, generator=g, device=device) * 2.5
+        feat += 0.5 * protos[lab].permute(0, 3, 1, 2)
+        keep = (torch.rand(B_PER_GPU, d, 1, 1, generator=g, device=device) >= 0.1).float() / 0.9
+        feat *= keep                                   # Dropout2d pattern of the EMA model in train() mode
+        hot = torch.nn.functional.one_hot(lab, C).permute(0, 3, 1, 2).float()
+        out = torch.randn(B_PER_GPU, C, H, W, generator=g, device=device) * 3 + 4 * hot
+        prior = (torch.randn(B_PER_GPU, C, H, W, generator=g, device=device) * 3 + 4 * hot).softmax(1)
+        sets.append((feat.contiguous(), prior.contiguous(), out.contiguous()))
+    return protos, sq_mean, counter, sets
+
+
+def cpu_reference_rate(torch, d, images, steps, warmup, threads):
+    """Times the oracle port of the reference (pseudo_labels hard + soft + ma) on host cores."""
+    from oracle import proto_oracle as po
+    torch.set_num_threads(threads)
+    case = po.synth_case(1234, images, d, H, W)
+    h = po.OracleHandler(**PARAMS)
+    h.prototypes, h.squared_mean, h.counter = case["protos"].clone(), case["sq_mean"].clone(), case["counter"].clone()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        po.fused_step(h, case["feat"], case["prior"], case["out"])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return images * H * W, times
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    images = 4 if args.d <= 256 else 1
+    px, times = cpu_reference_rate(torch, args.d, images, args.steps, args.warmup, threads)
+    dt = sum(times) / len(times)
+    value = px / dt
+    sample = f"{images} of {B_PER_GPU} images per step ({px} px), oracle port of the reference torch path, {threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.d, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(d, n_gpus):
+    return {"workload": (f"BASELINE configs[2]: batch-sharded prototype path, B={B_PER_GPU} images per GPU at 1024x512 "
+                         f"(65x129 stride-8 map), D={d}, C={C}, mahalanobis, hybrid_switch.yml parameters; step = fused "
+                         "hard+soft pseudo-labels + class sum/sumsq/count + statistics + EMA update"),
+            "B_per_gpu": B_PER_GPU, "D": d, "H": H, "W": W, "classes": C, "parallelism": f"batch-sharded x{n_gpus}",
+            "collective": "all-reduce of 19x(2D+1)+8 floats per step" if n_gpus > 1 else "none",
+            "l2_policy": "inputs larger than L2 (338 MB per step at D=256) and two rotating input sets"}
+
+
+def run_onda(args):
+    import torch
+    import torch.distributed as dist
+    from onda_b200 import prototype_handler, Monitor
+    from onda_b200 import _native as nat
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+    d = args.d
+    N = B_PER_GPU * H * W
+    lib = nat.load()
+
+    protos, sq_mean, counter, sets = gpu_inputs(torch, device, d, 2, 1234 + rank)
+    if world > 1:   # identical prototypes everywhere
+        for t in (protos, sq_mean, counter):
+            dist.broadcast(t, 0)
+    h = prototype_handler(process_group=group, impl=args.kernel, **PARAMS)
+    h.prototypes, h.squared_mean, h.counter = protos.clone(), sq_mean.clone(), counter.clone()
+
+    def step(i):
+        feat, prior, out = sets[i % len(sets)]
+        labels, soft = h.pseudo_labels_fused(feat, prior, out)
+        h.ma(feat, out)
+        return labels, soft
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ---------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    lib.onda_kernel_timing_enable(1)
+    launches0 = lib.onda_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = lib.onda_launch_count() - launches0
+    tot_ms, n_timed = nat.C.c_float(0), nat.C.c_int(0)
+    nat.check(lib.onda_kernel_timing_read(nat.C.byref(tot_ms), nat.C.byref(n_timed)))
+    lib.onda_kernel_timing_enable(0)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * N * args.steps / (ms * 1e-3)
+
+    # ---- end to end from pinned host buffers ------------------------------------------------
+    host = [tuple(x.cpu().pin_memory() for x in s) for s in sets]
+    dev_in = [tuple(torch.empty_like(x) for x in s) for s in sets]
+    lab_host = torch.empty((N, 1), dtype=torch.int64).pin_memory()
+    copy_stream = torch.cuda.Stream(device)
+    mon = Monitor(200, 0.003, "hamming")
+    h2d_bytes = sum(x.numel() * x.element_size() for x in host[0])
+    d2h_bytes = lab_host.numel() * 8 + nat.NUM_STATS * 4
+
+    def upload(i, after=None):
+        with torch.cuda.stream(copy_stream):
+            if after is not None:
+                copy_stream.wait_event(after)          # the buffer set's previous consumer has finished
+            for dst, src in zip(dev_in[i % 2], host[i % 2]):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def e2e_loop(k):
+        ev = upload(0)
+        prev_done = None
+        for i in range(k):
+            torch.cuda.current_stream().wait_event(ev)
+            feat, prior, out = dev_in[i % 2]
+            if i + 1 < k:
+                ev = upload(i + 1, prev_done)          # overlaps with this step's compute (other buffer set)
+            labels, soft = h.pseudo_labels_fused(feat, prior, out, confidence_monitor=mon)   # reads the stats (D2H)
+            h.ma(feat, out)
+            lab_host.copy_(labels, non_blocking=True)
+            prev_done = torch.cuda.Event()
+            prev_done.record()
+        torch.cuda.synchronize()
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(e2e_steps)
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * e2e_steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = hbm_peak()
+    kernel_ms = tot_ms.value / max(n_timed.value, 1)
+    alg_bytes = N * algorithmic_bytes_per_pixel(d)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(d, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": f"fused pseudo-label pass ({h.impl})", "kernel_ms": kernel_ms,
+                     "launches_timed": int(n_timed.value), "bytes_per_px": algorithmic_bytes_per_pixel(d),
+                     "peak_source": peak_src, "step_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+    }
+    if world == 1:
+        threads = os.cpu_count() or 1
+        images = 4 if d <= 256 else 1
+        px, times = cpu_reference_rate(torch, d, images, 3, 1, threads)
+        best = min(times)
+        line["cpu_baseline"] = {"value": px / best, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{images} of {B_PER_GPU} images ({px} px), best of 3 after 1 warm-up, "
+                                          "oracle port of the reference torch path"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="onda", choices=["onda", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--d", type=int, default=256, help="feature width (256 = real ProDA head, 2048 = stress size)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_onda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+/*
+ * onda_b200.h -- C ABI of the B200-native prototype pseudo-labelling path.
+ *
+ * theo2021/OnDA has no FFI of its own: the boundary of this path in the reference
+ * is the Python duck type `prototype_handler`
+ * (framework/domain_adaptation/methods/prototype_handler.py:8-166) and the
+ * `prototype_predictions()` methods that drive it
+ * (framework/domain_adaptation/methods/prototypes_hybrid_switch.py:45-101 and
+ * siblings).  The entry points below are what a ctypes binding for that class
+ * calls; each one names the reference lines it replaces.  INTEGRATION.md shows
+ * the reference-side stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - all arithmetic is fp32, labels are int64, tensors are dense and laid out
+ *     exactly as the reference holds them (feat/prior/logits NCHW, results
+ *     pixel-major (N, C) with n = (b*H + y)*W + x, prototype_handler.py:105-109);
+ *   - `stream` is a cudaStream_t passed as void*; nothing here allocates device
+ *     memory or synchronises with the host unless stated;
+ *   - return value: 0 on success, a negative ONDA_E* code otherwise;
+ *     onda_last_error() returns a thread-local description of the last failure.
+ */
+#ifndef ONDA_B200_H
+#define ONDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONDA_OK 0
+#define ONDA_EINVAL (-1)    /* bad argument (shape, null pointer, unsupported class count) */
+#define ONDA_ECUDA (-2)     /* a CUDA runtime call or launch failed */
+#define ONDA_EUNSUPPORTED (-3)
+
+#define ONDA_MAX_CLASSES 32 /* the reference uses 19 */
+#define ONDA_IGNORE_LABEL 255 /* prototype_handler.py:165 */
+
+#define ONDA_METRIC_EUCLIDEAN 0   /* prototype_handler.distance, :127-138 */
+#define ONDA_METRIC_MAHALANOBIS 1 /* prototype_handler.mahalanobis_distance, :111-125 */
+
+/* kernel selection for onda_pseudolabel_fused (ONDA_IMPL_AUTO picks tcgen05 when the shape allows) */
+#define ONDA_IMPL_AUTO 0
+#define ONDA_IMPL_SIMT 1    /* CUDA-core kernel, any shape */
+#define ONDA_IMPL_TCGEN05 2 /* 3xTF32 tcgen05.mma kernel, D % 32 == 0, D <= 512, C <= 24 */
+
+/* Number of statistic slots at the tail of a `sums` buffer (see onda_sums_floats). */
+#define ONDA_NUM_STATS 8
+#define ONDA_STAT_PROTO_CONF 0  /* sum_n max_k softmax(-d/tau)      prototype_handler.py:150 */
+#define ONDA_STAT_PRIOR_CONF 1  /* sum_n max_k prior[n,k]           prototypes_hybrid_switch.py:88 */
+#define ONDA_STAT_PL_CONF 2     /* sum_n max_k r[n,k]               prototypes_hybrid_switch.py:94-96 */
+#define ONDA_STAT_PL_PIXELS 3   /* #{n : label != 255}              prototypes.py:341-345 */
+#define ONDA_STAT_PIXELS 4      /* N (so that an all-reduced buffer carries its own denominator) */
+#define ONDA_STAT_ENTROPY 5     /* sum_n sum_k -r*log2(r+1e-30)/log2(C)   framework/utils/func.py:71-74 */
+
+/* ---- library / device info ------------------------------------------------ */
+int onda_abi_version(void);
+const char* onda_last_error(void);
+/* number of SMs of the current device (148 on B200); negative on error */
+int onda_sm_count(void);
+/* kernels launched by this library since it was loaded (process-wide, monotonically increasing) */
+unsigned long long onda_launch_count(void);
+
+/*
+ * Per-kernel timing of the dominant kernel (the fused pass) for the roofline report: when enabled,
+ * every onda_pseudolabel_fused call brackets its main kernel with CUDA events on the launch stream.
+ * onda_kernel_timing_read synchronises those events and returns the summed duration and the count
+ * since the last enable/reset.  Off by default; at most 4096 launches are recorded per window.
+ */
+int onda_kernel_timing_enable(int enable);
+int onda_kernel_timing_read(float* total_ms_host, int* launches_host);
+
+/* ---- buffer sizing (host, no CUDA calls) ----------------------------------- */
+/* floats in a distance table built by onda_build_distance_table */
+size_t onda_table_floats(int C, int D);
+/* floats in a `sums` buffer: [C*D sum | C*D sum of squares | C counts | ONDA_NUM_STATS stats] */
+size_t onda_sums_floats(int C, int D);
+/* bytes of scratch onda_pseudolabel_fused needs for this shape (per-CTA partials, split-D dots) */
+size_t onda_fused_workspace_bytes(int B, int D, int HW, int C, int impl);
+
+/* ---- prototype statistics ------------------------------------------------- */
+/*
+ * Builds the per-step distance table from the handler state: pooled std
+ * (global_var, prototype_handler.py:53-60), its inverse variance, the centring
+ * point, the scaled prototypes Q = w*(P-mu) and the per-class bias
+ * sum_j w_j (P_kj-mu_j)^2, so that d^2[n,k] = sum_j w_j (x_nj-mu_j)^2 - 2 (x_n-mu).Q_k + bias_k
+ * equals the reference's sum_j ((x_nj-P_kj)/sigma_j)^2 (prototype_handler.py:117-120, :132-135).
+ * `squared_mean` and `counter` may be NULL for ONDA_METRIC_EUCLIDEAN.
+ */
+int onda_build_distance_table(const float* prototypes, const float* squared_mean, const float* counter,
+                              int C, int D, int metric, float* table, void* stream);
+/* sigma[D]: pooled std of global_var(), prototype_handler.py:53-60 (reads it back out of a table) */
+int onda_table_global_std(const float* table, int C, int D, float* sigma_out, void* stream);
+/* out[C*D] = sqrt(squared_mean - prototypes^2): prototype_var(), prototype_handler.py:49-51 */
+int onda_prototype_std(const float* prototypes, const float* squared_mean, int C, int D, float* out, void* stream);
+
+/* ---- the fused pass --------------------------------------------------------- */
+/*
+ * One pass over feat (B, D, HW) that produces any subset of:
+ *   labels[N]  int64  argmax_k r, 255 where max_k r < thresh   (pseudo_labels hard,  :163-166)
+ *   soft[N*C]  f32    r = q*prior / sum_k q*prior, q = softmax_k(-(d-min d)/tau)  (:147, :159-160)
+ *   dist[N*C]  f32    d - min_k d                              (distance / mahalanobis_distance, :111-138)
+ *   sums       f32    class sum / sum of squares / count keyed by argmax_k logits[n,k]
+ *                     (get_proto_array on feat and feat**2, :76-90) plus the ONDA_STAT_* sums
+ * Outputs whose pointer is NULL are skipped; `prior` may be NULL only if labels and soft are;
+ * `logits` NULL skips the class sums.  `sums` must hold onda_sums_floats(C, D) floats and is
+ * fully overwritten (deterministically: fixed-order combine of per-CTA partials).
+ * `workspace` must hold onda_fused_workspace_bytes(...) bytes.
+ */
+int onda_pseudolabel_fused(const float* feat, const float* prior, const float* logits, const float* table,
+                           int B, int D, int HW, int C, float tau, float thresh,
+                           int64_t* labels, float* soft, float* dist, float* sums,
+                           void* workspace, size_t workspace_bytes, int impl, void* stream);
+
+/* ---- prototype updates ------------------------------------------------------ */
+/* ma(): P_k <- P_k*rho_k + (1-rho_k)*sum_k/max(cnt_k,1), rho_k = lambda if cnt_k>0 else 1; same for the
+ * squared mean; counter untouched.  prototype_handler.py:88-99. */
+int onda_ema_update(float* prototypes, float* squared_mean, const float* sums, int C, int D, float ma_lambda,
+                    void* stream);
+/* append(): counter += cnt; P += (sum - P*cnt)/max(counter,1); likewise S.  prototype_handler.py:62-74. */
+int onda_append_update(float* prototypes, float* squared_mean, float* counter, const float* sums, int C, int D,
+                       void* stream);
+
+/* ---- switch statistics / prior mix ------------------------------------------ */
+/*
+ * prior[b,k,p] = sum_i coef[i] * softmax_k(logits_i[b,:,p]) over the non-NULL inputs (i < 3), written to
+ * `prior_out` (may be NULL: statistics only), and stats_out[0..2] = sum_n max_k softmax(logits_i)[n,k],
+ * stats_out[3] = sum_n max_k prior[n,k], stats_out[4] = N.  Replaces the softmax / max / mean chains of
+ * prototypes_hybrid_switch.py:52-88, prototypes_hswitch.py:30-68, prototypes_vswitch.py:40-70 and
+ * prototypes.py:213-250.  stats_out holds 8 floats and is overwritten.
+ */
+int onda_prior_mix_stats(const float* logits0, const float* logits1, const float* logits2,
+                         float coef0, float coef1, float coef2, int B, int C, int HW,
+                         float* prior_out, float* stats_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+size_t onda_prior_workspace_bytes(int B, int C, int HW);
+
+/* ---- multi-GPU ---------------------------------------------------------------- */
+/*
+ * One-shot sum all-reduce of `n` floats over `world` ranks whose buffers are mapped into this
+ * process (NVLink peer memory).  peer_bufs[r] / peer_flags[r] are DEVICE-visible pointers to rank
+ * r's staging buffer (n floats) and flag word; every rank pushes nothing and instead reads all
+ * peers' staging buffers in rank order 0..world-1 after a flag handshake, so every rank computes
+ * bit-identical sums.  `local` (n floats) is this rank's input and receives the result.
+ * Replaces nothing in the reference (it is single-GPU); see DESIGN.md section (e).
+ */
+int onda_allreduce_oneshot(float* local, size_t n, int rank, int world, void* const* peer_bufs_host,
+                           void* const* peer_flags_host, uint32_t epoch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONDA_B200_H */

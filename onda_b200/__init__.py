@@ -1,0 +1,16 @@
+"""onda_b200: B200-native implementation of OnDA's prototype pseudo-labelling hot path.
+
+Public surface (mirrors the reference's names):
+
+* ``prototype_handler`` -- drop-in for ``framework.domain_adaptation.methods.prototype_handler``
+* ``Monitor``, ``HybridSelect``, ``DevSelect``, ``static_share`` -- host-side switch logic
+* ``onda_b200.methods`` -- ``prototype_predictions`` for the base / h-switch / v-switch / hybrid
+  method classes, to be bound onto the reference's ``online_proDA`` subclasses
+
+Importing the package loads ``libonda_b200.so`` lazily (on first handler construction); if the
+library has not been built the constructor raises -- there is no CPU or PyTorch fallback.
+"""
+from .switching import Monitor, HybridSelect, DevSelect, static_share  # noqa: F401
+from .handler import prototype_handler  # noqa: F401
+
+__all__ = ["prototype_handler", "Monitor", "HybridSelect", "DevSelect", "static_share"]

@@ -1,0 +1,523 @@
+// extern "C" entry points of include/onda_b200.h plus the small kernels around the fused pass:
+// distance-table build, fixed-order partial reduction, EMA / cumulative prototype updates and
+// the prior-mix / switch-statistics kernel.
+#include <stdarg.h>
+#include <string.h>
+
+#include "epilogue.cuh"
+
+namespace onda {
+
+// ---- error plumbing -----------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return ONDA_ECUDA;
+}
+
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+// ---- optional kernel timing (roofline report) ----------------------------------------------
+constexpr int kMaxTimed = 4096;
+static bool g_timing = false;
+static int g_timed = 0;
+static cudaEvent_t g_ev[kMaxTimed][2];
+static int g_ev_made = 0;
+
+void timing_begin(cudaStream_t s) {
+    if (!g_timing || g_timed >= kMaxTimed) return;
+    while (g_ev_made <= g_timed) {
+        cudaEventCreate(&g_ev[g_ev_made][0]);
+        cudaEventCreate(&g_ev[g_ev_made][1]);
+        ++g_ev_made;
+    }
+    cudaEventRecord(g_ev[g_timed][0], s);
+}
+void timing_end(cudaStream_t s) {
+    if (!g_timing || g_timed >= kMaxTimed) return;
+    cudaEventRecord(g_ev[g_timed][1], s);
+    ++g_timed;
+}
+
+static int cached_sm_count() {
+    static int sms = 0;
+    if (sms > 0) return sms;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    sms = v;
+    return sms;
+}
+
+// ---- distance table ----------------------------------------------------------------------
+// One CTA: the whole state is C*D <= 32*4096 floats.  All reductions are fixed-order.
+constexpr int kTableThreads = 256;
+
+__global__ void __launch_bounds__(kTableThreads) table_kernel(const float* __restrict__ P, const float* __restrict__ S,
+                                                              const float* __restrict__ cnt, int C, int D, int metric,
+                                                              float* __restrict__ table) {
+    const TableLayout T = table_layout(C, D);
+    __shared__ double bias_part[kTableThreads / 32][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool mahal = metric == ONDA_METRIC_MAHALANOBIS;
+    double total = 0.0;
+    if (mahal)
+        for (int k = 0; k < C; ++k) total += (double)cnt[k];
+    double b[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) b[k] = 0.0;
+    for (int j = tid; j < T.Dp; j += kTableThreads) {
+        float sigma = 0.f, wf = 0.f, muf = 0.f;
+        if (j < D) {
+            double gm = 0.0, gsq = 0.0, mean = 0.0;
+            for (int k = 0; k < C; ++k) {
+                const double pk = (double)P[(size_t)k * D + j];
+                mean += pk;
+                if (mahal) {
+                    const double ck = (double)cnt[k];
+                    gm += pk * ck / total;                          // global_var(): prototype_handler.py:57-59
+                    gsq += (double)S[(size_t)k * D + j] * ck / total;  // :54-56
+                }
+            }
+            if (mahal) {
+                sigma = (float)sqrt(gsq - gm * gm);                  // :60
+                wf = (float)(1.0 / ((double)sigma * (double)sigma));
+                muf = (float)gm;
+            } else {
+                sigma = 1.f;
+                wf = 1.f;
+                muf = (float)(mean / C);
+            }
+        }
+        table[T.off_sigma + j] = sigma;
+        table[T.off_w + j] = wf;
+        table[T.off_mu + j] = muf;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if (k < T.CP) {
+                float qf = 0.f;
+                if (j < D && k < C) {
+                    const double diff = (double)P[(size_t)k * D + j] - (double)muf;
+                    qf = (float)((double)wf * diff);
+                    b[k] += (double)wf * diff * diff;
+                }
+                table[T.off_q + (size_t)j * T.CP + k] = qf;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        double v = b[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) bias_part[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        double v = 0.0;
+        for (int w = 0; w < kTableThreads / 32; ++w) v += bias_part[w][tid];
+        table[T.off_bias + tid] = (float)v;
+    }
+    // TF32 split of -2*Q, class-major, for the tcgen05 kernel (rows >= C are zero)
+    __syncthreads();
+    for (int i = tid; i < 24 * T.Dp; i += kTableThreads) {
+        const int k = i / T.Dp, j = i - k * T.Dp;
+        float v = 0.f;
+        if (k < T.CP && k < C) v = -2.f * table[T.off_q + (size_t)j * T.CP + k];
+        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+        table[T.off_qhi + i] = hi;
+        table[T.off_qlo + i] = v - hi;
+    }
+}
+
+__global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+__global__ void class_std_kernel(const float* __restrict__ P, const float* __restrict__ S, float* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sqrtf(S[i] - P[i] * P[i]);  // prototype_var(): prototype_handler.py:49-51
+}
+
+// ---- fixed-order combine of per-CTA partials ----------------------------------------------
+// Block = 32 elements x 8 partial-lanes; lane g sums CTAs g, g+8, ... then the 8 lane sums are
+// added in lane order: the summation tree depends only on (n_cta), never on scheduling.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ cta_partials, int n_cta,
+                                                              size_t stride, int class_elems, int has_sums,
+                                                              const float* __restrict__ stat_partials, int n_stat,
+                                                              int has_stats, float* __restrict__ out) {
+    __shared__ double part[8][32];
+    const int el = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + el;
+    const int total = class_elems + kStatSlots;
+    double s = 0.0;
+    if (e < class_elems) {
+        if (has_sums)
+            for (int c = g; c < n_cta; c += 8) s += (double)cta_partials[(size_t)c * stride + e];
+    } else if (e < total) {
+        if (has_stats)
+            for (int c = g; c < n_stat; c += 8) s += (double)stat_partials[(size_t)c * kStatSlots + (e - class_elems)];
+    }
+    part[g][el] = s;
+    __syncthreads();
+    if (g == 0 && e < total) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][el];
+        out[e] = (float)t;
+    }
+}
+
+// ---- prototype updates -----------------------------------------------------------------------
+__global__ void ema_kernel(float* __restrict__ P, float* __restrict__ S, const float* __restrict__ sums, int C, int D,
+                           float lam) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * D) return;
+    const int k = i / D;
+    const float cnt = sums[(size_t)2 * C * D + k];
+    const float rho = cnt > 0.f ? lam : 1.f;        // lambda ** (cnt > 0), prototype_handler.py:92
+    const float one_m = __fsub_rn(1.f, rho);
+    const float den = cnt > 0.f ? cnt : 1.f;        // mask(), :21, :93
+    const float m1 = __fdiv_rn(sums[i], den);
+    const float m2 = __fdiv_rn(sums[(size_t)C * D + i], den);
+    P[i] = __fadd_rn(__fmul_rn(P[i], rho), __fmul_rn(one_m, m1));  // :94-96
+    S[i] = __fadd_rn(__fmul_rn(S[i], rho), __fmul_rn(one_m, m2));  // :97-99
+}
+
+__global__ void append_kernel(float* __restrict__ P, float* __restrict__ S, float* __restrict__ counter,
+                              const float* __restrict__ sums, int C, int D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * D) return;
+    const int k = i / D;
+    const float cnt = sums[(size_t)2 * C * D + k];
+    const float tot = __fadd_rn(counter[k], cnt);   // counter += sums, prototype_handler.py:66
+    const float den = tot > 0.f ? tot : 1.f;        // :67
+    const float d1 = __fsub_rn(sums[i], __fmul_rn(P[i], cnt));                  // :71
+    const float d2 = __fsub_rn(sums[(size_t)C * D + i], __fmul_rn(S[i], cnt));  // :72
+    P[i] = __fadd_rn(P[i], __fdiv_rn(d1, den));     // :73
+    S[i] = __fadd_rn(S[i], __fdiv_rn(d2, den));     // :74
+}
+
+__global__ void counter_add_kernel(float* __restrict__ counter, const float* __restrict__ sums, int C, int D) {
+    const int k = threadIdx.x;
+    if (k < C) counter[k] = __fadd_rn(counter[k], sums[(size_t)2 * C * D + k]);
+}
+
+// ---- prior mix + switch statistics ----------------------------------------------------------
+constexpr int kPriorThreads = 256;
+
+template <int CP>
+__global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* __restrict__ l0, const float* __restrict__ l1,
+                                                                  const float* __restrict__ l2, float c0, float c1, float c2,
+                                                                  int B, int C, int HW, float* __restrict__ prior_out,
+                                                                  float* __restrict__ partials, unsigned* __restrict__ ticket,
+                                                                  float* __restrict__ stats_out) {
+    __shared__ float red[kPriorThreads / 32][kStatSlots];
+    __shared__ bool last;
+    const long long N = (long long)B * HW;
+    const float* src[3] = {l0, l1, l2};
+    const float coef[3] = {c0, c1, c2};
+    float st[kStatSlots];
+#pragma unroll
+    for (int s = 0; s < kStatSlots; ++s) st[s] = 0.f;
+    for (long long n = (long long)blockIdx.x * kPriorThreads + threadIdx.x; n < N; n += (long long)gridDim.x * kPriorThreads) {
+        const long long b = n / HW, q = n - b * HW;
+        const long long off = (b * C) * (long long)HW + q;
+        float mix[CP];
+#pragma unroll
+        for (int k = 0; k < CP; ++k) mix[k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (src[i] == nullptr) continue;
+            float z[CP];
+            float zmax = -__int_as_float(0x7f800000);
+#pragma unroll
+            for (int k = 0; k < CP; ++k) {
+                if (k < C) {
+                    z[k] = __ldg(src[i] + off + (long long)k * HW);
+                    if (z[k] > zmax || z[k] != z[k]) zmax = z[k];
+                }
+            }
+            float esum = 0.f;
+#pragma unroll
+            for (int k = 0; k < CP; ++k) {
+                if (k < C) {
+                    z[k] = exp2f((z[k] - zmax) * 1.4426950408889634f);
+                    esum += z[k];
+                }
+            }
+            float pmax = -1.f;
+#pragma unroll
+            for (int k = 0; k < CP; ++k) {
+                if (k < C) {
+                    const float pk = __fdiv_rn(z[k], esum);   // softmax(axis=1), prototypes_hybrid_switch.py:53
+                    if (torch_greater(pk, pmax)) pmax = pk;
+                    mix[k] = __fadd_rn(mix[k], __fmul_rn(coef[i], pk));  // prior (+)= lambda * softmax, :56, :64, :84
+                }
+            }
+            st[i] += pmax;                                    // .max(axis=1)[0].mean(), :54, :62, :81
+        }
+        float mmax = -__int_as_float(0x7f800000);
+#pragma unroll
+        for (int k = 0; k < CP; ++k) {
+            if (k < C) {
+                if (torch_greater(mix[k], mmax)) mmax = mix[k];
+                if (prior_out != nullptr) prior_out[off + (long long)k * HW] = mix[k];
+            }
+        }
+        st[3] += mmax;                                        // {"prior": prior.max(axis=1)[0].mean()}, :88
+        st[4] += 1.f;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < kStatSlots; ++s) {
+        const float v = warp_sum(st[s]);
+        if (lane == 0) red[warp][s] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kStatSlots) {
+        float v = 0.f;
+        for (int w = 0; w < kPriorThreads / 32; ++w) v += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * kStatSlots + threadIdx.x] = v;
+    }
+    // last CTA to arrive folds the per-CTA rows in CTA order (deterministic), then re-arms the ticket
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        if (threadIdx.x < kStatSlots) {
+            double v = 0.0;
+            for (unsigned c = 0; c < gridDim.x; ++c) v += (double)__ldcg(partials + (size_t)c * kStatSlots + threadIdx.x);
+            stats_out[threadIdx.x] = (float)v;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+}  // namespace onda
+
+using namespace onda;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int onda_abi_version(void) { return 1; }
+
+const char* onda_last_error(void) { return g_err; }
+
+int onda_sm_count(void) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return ONDA_ECUDA;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return ONDA_ECUDA;
+    return v;
+}
+
+unsigned long long onda_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int onda_kernel_timing_enable(int enable) {
+    g_timing = enable != 0;
+    g_timed = 0;
+    return ONDA_OK;
+}
+
+int onda_kernel_timing_read(float* total_ms_host, int* launches_host) {
+    ONDA_REQUIRE(total_ms_host && launches_host, "onda_kernel_timing_read: null pointer");
+    float total = 0.f;
+    for (int i = 0; i < g_timed; ++i) {
+        ONDA_CUDA_TRY(cudaEventSynchronize(g_ev[i][1]));
+        float ms = 0.f;
+        ONDA_CUDA_TRY(cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]));
+        total += ms;
+    }
+    *total_ms_host = total;
+    *launches_host = g_timed;
+    g_timed = 0;
+    return ONDA_OK;
+}
+
+size_t onda_table_floats(int C, int D) { return table_layout(C, D).total; }
+
+size_t onda_sums_floats(int C, int D) { return sums_floats(C, D); }
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct Workspace {
+    size_t off_cta, off_stat, off_dots, total;
+    int max_cta, max_stat;
+};
+
+static Workspace fused_workspace(int B, int D, int HW, int C) {
+    const int sms = cached_sm_count();
+    const SimtPlan pl = plan_simt(B, D, HW, C, sms, true, true);
+    Workspace w;
+    w.max_cta = 2 * sms > pl.grid_x ? 2 * sms : pl.grid_x;
+    w.max_stat = 4 * sms;
+    w.off_cta = 0;
+    w.off_stat = align256(w.off_cta + (size_t)w.max_cta * sums_floats(C, D) * sizeof(float));
+    w.off_dots = align256(w.off_stat + (size_t)w.max_stat * kStatSlots * sizeof(float));
+    const size_t dots = pl.nslices > 1 ? (size_t)pl.nslices * (padded_classes(C) + 1) * (size_t)B * HW * sizeof(float) : 0;
+    w.total = align256(w.off_dots + dots);
+    return w;
+}
+
+size_t onda_fused_workspace_bytes(int B, int D, int HW, int C, int impl) {
+    (void)impl;
+    if (B <= 0 || D <= 0 || HW <= 0 || C <= 0 || C > ONDA_MAX_CLASSES) return 0;
+    return fused_workspace(B, D, HW, C).total;
+}
+
+int onda_build_distance_table(const float* prototypes, const float* squared_mean, const float* counter, int C, int D,
+                              int metric, float* table, void* stream) {
+    ONDA_REQUIRE(prototypes && table, "onda_build_distance_table: null pointer");
+    ONDA_REQUIRE(C > 0 && C <= ONDA_MAX_CLASSES && D > 0, "onda_build_distance_table: unsupported shape C=%d D=%d", C, D);
+    ONDA_REQUIRE(metric == ONDA_METRIC_EUCLIDEAN || metric == ONDA_METRIC_MAHALANOBIS,
+                 "onda_build_distance_table: unexpected value for attribute distance_metric (%d)", metric);
+    if (metric == ONDA_METRIC_MAHALANOBIS)
+        ONDA_REQUIRE(squared_mean && counter, "onda_build_distance_table: mahalanobis needs squared_mean and counter");
+    table_kernel<<<1, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric, table);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int onda_table_global_std(const float* table, int C, int D, float* sigma_out, void* stream) {
+    ONDA_REQUIRE(table && sigma_out && C > 0 && D > 0, "onda_table_global_std: bad argument");
+    const TableLayout T = table_layout(C, D);
+    copy_kernel<<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(table + T.off_sigma, sigma_out, D);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int onda_prototype_std(const float* prototypes, const float* squared_mean, int C, int D, float* out, void* stream) {
+    ONDA_REQUIRE(prototypes && squared_mean && out && C > 0 && D > 0, "onda_prototype_std: bad argument");
+    const int n = C * D;
+    class_std_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, out, n);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int onda_pseudolabel_fused(const float* feat, const float* prior, const float* logits, const float* table, int B, int D,
+                           int HW, int C, float tau, float thresh, int64_t* labels, float* soft, float* dist,
+                           float* sums, void* workspace, size_t workspace_bytes, int impl, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ONDA_REQUIRE(feat && sums && workspace, "onda_pseudolabel_fused: null feat/sums/workspace");
+    ONDA_REQUIRE(B > 0 && D > 0 && HW > 0, "onda_pseudolabel_fused: empty shape B=%d D=%d HW=%d", B, D, HW);
+    ONDA_REQUIRE(C > 0 && C <= ONDA_MAX_CLASSES, "onda_pseudolabel_fused: %d classes unsupported (max %d)", C,
+                 ONDA_MAX_CLASSES);
+    const bool want_dist = labels || soft || dist;
+    const bool want_sums = logits != nullptr;
+    ONDA_REQUIRE(want_dist || want_sums, "onda_pseudolabel_fused: nothing to compute");
+    ONDA_REQUIRE(!want_dist || table, "onda_pseudolabel_fused: distance outputs need a distance table");
+    ONDA_REQUIRE(!(labels || soft) || prior, "onda_pseudolabel_fused: labels/soft need a prior");
+    ONDA_REQUIRE(impl == ONDA_IMPL_AUTO || impl == ONDA_IMPL_SIMT || impl == ONDA_IMPL_TCGEN05,
+                 "onda_pseudolabel_fused: unknown impl %d", impl);
+    ONDA_REQUIRE(impl != ONDA_IMPL_TCGEN05, "onda_pseudolabel_fused: tcgen05 path not built for this shape");
+    const Workspace ws = fused_workspace(B, D, HW, C);
+    ONDA_REQUIRE(workspace_bytes >= ws.total, "onda_pseudolabel_fused: workspace too small (%zu < %zu)", workspace_bytes,
+                 ws.total);
+    const int sms = cached_sm_count();
+    const SimtPlan pl = plan_simt(B, D, HW, C, sms, want_dist, want_sums);
+
+    FusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.feat = feat; p.prior = prior; p.logits = logits; p.table = table;
+    p.B = B; p.D = D; p.HW = HW; p.C = C; p.N = (long long)B * HW;
+    p.tau = tau; p.thresh = thresh;
+    p.labels = (long long*)labels; p.soft = soft; p.dist = dist;
+    char* base = (char*)workspace;
+    p.cta_partials = (float*)(base + ws.off_cta);
+    p.stat_partials = (float*)(base + ws.off_stat);
+    p.dots_scratch = (float*)(base + ws.off_dots);
+    p.nslices = pl.nslices; p.slice_channels = pl.DS; p.tiles = pl.tiles;
+
+    int rc = launch_fused_simt(p, pl, want_dist, want_sums, stream);
+    if (rc != ONDA_OK) return rc;
+
+    const int class_elems = 2 * C * D + C;
+    const int n_stat = want_dist ? (pl.nslices > 1 ? pl.finish_grid : pl.grid_x) : 0;
+    const int blocks = (class_elems + kStatSlots + 31) / 32;
+    reduce_partials_kernel<<<blocks, 256, 0, stream>>>(p.cta_partials, pl.grid_x, sums_floats(C, D), class_elems,
+                                                       want_sums ? 1 : 0, p.stat_partials, n_stat, want_dist ? 1 : 0, sums);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int onda_ema_update(float* prototypes, float* squared_mean, const float* sums, int C, int D, float ma_lambda,
+                    void* stream) {
+    ONDA_REQUIRE(prototypes && squared_mean && sums && C > 0 && D > 0, "onda_ema_update: bad argument");
+    const int n = C * D;
+    ema_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, sums, C, D, ma_lambda);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int onda_append_update(float* prototypes, float* squared_mean, float* counter, const float* sums, int C, int D,
+                       void* stream) {
+    ONDA_REQUIRE(prototypes && squared_mean && counter && sums && C > 0 && C <= ONDA_MAX_CLASSES && D > 0,
+                 "onda_append_update: bad argument");
+    const int n = C * D;
+    append_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, sums, C, D);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, sums, C, D);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+size_t onda_prior_workspace_bytes(int B, int C, int HW) {
+    (void)B; (void)C; (void)HW;
+    return 256 + (size_t)4 * cached_sm_count() * kStatSlots * sizeof(float);
+}
+
+int onda_prior_mix_stats(const float* logits0, const float* logits1, const float* logits2, float coef0, float coef1,
+                         float coef2, int B, int C, int HW, float* prior_out, float* stats_out, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    ONDA_REQUIRE(stats_out && workspace, "onda_prior_mix_stats: null stats/workspace");
+    ONDA_REQUIRE(logits0 || logits1 || logits2, "onda_prior_mix_stats: no input");
+    ONDA_REQUIRE(B > 0 && HW > 0 && C > 0 && C <= ONDA_MAX_CLASSES, "onda_prior_mix_stats: bad shape");
+    ONDA_REQUIRE(workspace_bytes >= onda_prior_workspace_bytes(B, C, HW), "onda_prior_mix_stats: workspace too small");
+    const long long N = (long long)B * HW;
+    const int sms = cached_sm_count();
+    long long want = (N + kPriorThreads - 1) / kPriorThreads;
+    const int grid = (int)(want < 4LL * sms ? want : 4LL * sms);
+    unsigned* ticket = (unsigned*)workspace;  // zero on first use; the kernel re-arms it
+    float* partials = (float*)((char*)workspace + 256);
+    if (padded_classes(C) == 20)
+        prior_mix_kernel<20><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>(logits0, logits1, logits2, coef0, coef1, coef2, B,
+                                                                               C, HW, prior_out, partials, ticket, stats_out);
+    else
+        prior_mix_kernel<32><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>(logits0, logits1, logits2, coef0, coef1, coef2, B,
+                                                                               C, HW, prior_out, partials, ticket, stats_out);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int onda_allreduce_oneshot(float* local, size_t n, int rank, int world, void* const* peer_bufs_host,
+                           void* const* peer_flags_host, uint32_t epoch, void* stream) {
+    (void)local; (void)n; (void)rank; (void)world; (void)peer_bufs_host; (void)peer_flags_host; (void)epoch; (void)stream;
+    set_error("onda_allreduce_oneshot: not built yet");
+    return ONDA_EUNSUPPORTED;
+}
+
+}  // extern "C"
