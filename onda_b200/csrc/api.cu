@@ -147,7 +147,7 @@ __global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ d
 
 __global__ void class_std_kernel(const float* __restrict__ P, const float* __restrict__ S, float* __restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = sqrtf(S[i] - P[i] * P[i]);  // prototype_var(): prototype_handler.py:49-51
+    if (i < n) out[i] = sqrtf(__fsub_rn(S[i], __fmul_rn(P[i], P[i])));  // prototype_var(): prototype_handler.py:49-51
 }
 
 // ---- fixed-order combine of per-CTA partials ----------------------------------------------

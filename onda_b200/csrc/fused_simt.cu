@@ -7,6 +7,9 @@
 //   * register tiling: each Q row read from shared memory feeds 4 pixels x CP classes of FMAs;
 //   * deterministic class sums without atomics: the per-class accumulators of a channel are
 //     only ever touched by the one warp that owns the channel, in tile order.
+// The class sums use a warp-private shared-memory transposition tile: after a 32-channel block has
+// been staged, lane = channel walks the 128 pixels with run-length accumulation (cost independent
+// of how many classes a tile contains).
 // The four partial dot-product sets are combined through shared memory in warp order, then
 // thread t finishes pixel t (epilogue.cuh).  With more than one channel slice (large D, or few
 // tiles) the partial dots go to a scratch array and split_finish_kernel completes the pixels.
@@ -17,19 +20,23 @@ namespace onda {
 constexpr int kSimtThreads = 128;
 constexpr int kChunk = 8;  // channels per register chunk
 
+constexpr int kTRow = kTilePixels + 4;  // padded row of the transposition tile (conflict-free LDS.128 by channel)
+
 struct SimtSmem {
     int DS;  // channels in a slice (multiple of 32)
-    size_t q, mu, w, acc, dots, ys, cnt, red, total;
+    size_t mu, w, acc, tile, ys, cnt, red, total;
 };
 __host__ __device__ inline SimtSmem simt_smem(int DS, int C, int CP, bool dist, bool sums) {
     SimtSmem s;
     s.DS = DS;
-    s.q = 0;
-    s.mu = s.q + (dist ? (size_t)DS * CP : 0);
+    s.mu = 0;
     s.w = s.mu + (dist ? DS : 0);
     s.acc = s.w + (dist ? DS : 0);
-    s.dots = s.acc + (sums ? (size_t)2 * C * DS : 0);
-    s.ys = s.dots + (dist ? (size_t)4 * kTilePixels * (CP + 1) : 0);
+    s.tile = s.acc + (sums ? (size_t)2 * C * DS : 0);
+    // the per-warp transposition tiles [4][32][kTRow] and the dot-product staging [4][128][CP+1] share storage
+    const size_t t_tile = sums ? (size_t)4 * 32 * kTRow : 0;
+    const size_t t_dots = dist ? (size_t)4 * kTilePixels * (CP + 1) : 0;
+    s.ys = s.tile + (t_tile > t_dots ? t_tile : t_dots);
     s.cnt = s.ys + kTilePixels;
     s.red = s.cnt + 32;
     s.total = s.red + 4 * kStatSlots;
@@ -44,21 +51,18 @@ __global__ void __launch_bounds__(kSimtThreads, 2) fused_simt_kernel(const Fused
     const int DS = p.slice_channels;
     const int s0 = blockIdx.y * DS;
     const SimtSmem L = simt_smem(DS, C, CP, DIST, SUMS);
-    float* Qs = smem + L.q;
     float* mus = smem + L.mu;
     float* wsm = smem + L.w;
     float* acc = smem + L.acc;
-    float* dots = smem + L.dots;
+    float* dots = smem + L.tile;
+    float* Tw = smem + L.tile + (size_t)warp * 32 * kTRow;   // this warp's [32 channels][kTRow pixels] tile
     int* ys = reinterpret_cast<int*>(smem + L.ys);
     int* cnt = reinterpret_cast<int*>(smem + L.cnt);
     float* red = smem + L.red;
 
     const TableLayout T = table_layout(C, D);
+    const float* Qg = p.table + T.off_q;   // [Dp][CP] rows, read through L1 (uniform 16-byte loads)
     if (DIST) {
-        for (int i = tid; i < DS * CP; i += kSimtThreads) {
-            int ch = s0 + i / CP;
-            Qs[i] = ch < T.Dp ? p.table[T.off_q + (size_t)s0 * CP + i] : 0.f;
-        }
         for (int i = tid; i < DS; i += kSimtThreads) {
             int ch = s0 + i;
             mus[i] = ch < T.Dp ? p.table[T.off_mu + ch] : 0.f;
@@ -96,11 +100,10 @@ __global__ void __launch_bounds__(kSimtThreads, 2) fused_simt_kernel(const Fused
             }
             ys[tid] = arg;
         }
-        __syncthreads();  // ys visible; previous tile's readers of dots/ys are done
+        __syncthreads();  // ys visible; previous tile's readers of the staging area are done
 
         const float* fptr[4];
         bool valid[4];
-        int y[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const long long n = tile_base + 32 * i + lane;
@@ -108,26 +111,25 @@ __global__ void __launch_bounds__(kSimtThreads, 2) fused_simt_kernel(const Fused
             const long long nn = valid[i] ? n : 0;
             const long long b = nn / HW, q = nn - b * HW;
             fptr[i] = p.feat + (b * D) * (long long)HW + q;
-            y[i] = SUMS ? ys[32 * i + lane] : -1;
         }
-        unsigned class_mask = 0;
-        if (SUMS) {
+        if (SUMS && warp == 0 && blockIdx.y == 0) {  // pixel counts per class, once per tile
+            unsigned class_mask = 0;
+            int y[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) class_mask |= (y[i] >= 0) ? (1u << y[i]) : 0u;
+            for (int i = 0; i < 4; ++i) {
+                y[i] = ys[32 * i + lane];
+                class_mask |= (y[i] >= 0) ? (1u << y[i]) : 0u;
+            }
             class_mask = __reduce_or_sync(0xffffffffu, class_mask);
-            if (warp == 0 && blockIdx.y == 0) {  // pixel counts per class, once per tile
-                unsigned rem = class_mask;
-                while (rem) {
-                    const int k = __ffs(rem) - 1;
-                    rem &= rem - 1;
-                    int c = 0;
+            while (class_mask) {
+                const int k = __ffs(class_mask) - 1;
+                class_mask &= class_mask - 1;
+                int c = 0;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) c += __popc(__ballot_sync(0xffffffffu, y[i] == k));
-                    if (lane == 0) cnt[k] += c;
-                }
+                for (int i = 0; i < 4; ++i) c += __popc(__ballot_sync(0xffffffffu, y[i] == k));
+                if (lane == 0) cnt[k] += c;
             }
         }
-        const bool uniform = __popc(class_mask) <= 1;
 
         float dot[4][CP];
         float A[4];
@@ -152,80 +154,89 @@ __global__ void __launch_bounds__(kSimtThreads, 2) fused_simt_kernel(const Fused
             }
         };
         if (cbeg < cend) load_chunk(cbeg);
-        for (int c0 = cbeg; c0 < cend; c0 += kChunk) {
-            float x[4][kChunk];
+        for (int blk = cbeg; blk < cend; blk += 32) {       // 32-channel block = one transposition tile
+            const int bend = min(blk + 32, cend);
+            for (int c0 = blk; c0 < bend; c0 += kChunk) {
+                float x[4][kChunk];
 #pragma unroll
-            for (int j = 0; j < kChunk; ++j)
+                for (int j = 0; j < kChunk; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) x[i][j] = xn[i][j];
-            if (c0 + kChunk < cend) load_chunk(c0 + kChunk);  // prefetch: 32 loads in flight per thread
+                    for (int i = 0; i < 4; ++i) x[i][j] = xn[i][j];
+                if (c0 + kChunk < cend) load_chunk(c0 + kChunk);  // prefetch: 32 loads in flight per thread
 
-            if (DIST) {
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) {
-                    const int cl = c0 + j - s0;
-                    const float m = mus[cl], wv = wsm[cl];
-                    float qv[CP];
-                    const float4* q4 = reinterpret_cast<const float4*>(Qs + cl * CP);
-#pragma unroll
-                    for (int k4 = 0; k4 < CP / 4; ++k4) {
-                        float4 v = q4[k4];
-                        qv[4 * k4 + 0] = v.x; qv[4 * k4 + 1] = v.y; qv[4 * k4 + 2] = v.z; qv[4 * k4 + 3] = v.w;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float xc = x[i][j] - m;
-                        A[i] = fmaf(xc * xc, wv, A[i]);
-#pragma unroll
-                        for (int k = 0; k < CP; ++k) dot[i][k] = fmaf(xc, qv[k], dot[i][k]);
-                    }
-                }
-            }
-
-            if (SUMS) {
-                // warp-level reduce-scatter of 8 channel sums + 8 channel sums of squares over the
-                // 128 pixels of the tile, once per class present in the tile (once, unmasked, when
-                // the tile is class-uniform).  Lane pair (2i, 2i+1) ends with value index i.
-                unsigned rem = class_mask;
-                while (rem) {
-                    const int k = __ffs(rem) - 1;
-                    rem &= rem - 1;
-                    float v[16];
+                if (DIST) {
 #pragma unroll
                     for (int j = 0; j < kChunk; ++j) {
-                        float s = 0.f, s2 = 0.f;
+                        const int cl = c0 + j - s0;
+                        const float m = mus[cl], wv = wsm[cl];
+                        float qv[CP];
+                        const float4* q4 = reinterpret_cast<const float4*>(Qg + (size_t)(c0 + j) * CP);
+#pragma unroll
+                        for (int k4 = 0; k4 < CP / 4; ++k4) {
+                            float4 v = __ldg(q4 + k4);
+                            qv[4 * k4 + 0] = v.x; qv[4 * k4 + 1] = v.y; qv[4 * k4 + 2] = v.z; qv[4 * k4 + 3] = v.w;
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float xv = (uniform || y[i] == k) ? x[i][j] : 0.f;
-                            s += xv;
-                            s2 = fmaf(xv, xv, s2);
-                        }
-                        v[j] = s;
-                        v[kChunk + j] = s2;
-                    }
+                            const float xc = x[i][j] - m;
+                            A[i] = fmaf(xc * xc, wv, A[i]);
 #pragma unroll
-                    for (int half = 8; half >= 1; half >>= 1) {
-                        const bool up = (lane & (2 * half)) != 0;
-#pragma unroll
-                        for (int t2 = 0; t2 < half; ++t2) {
-                            const float send = up ? v[t2] : v[t2 + half];
-                            const float keep = up ? v[t2 + half] : v[t2];
-                            v[t2] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * half);
+                            for (int k = 0; k < CP; ++k) dot[i][k] = fmaf(xc, qv[k], dot[i][k]);
                         }
-                    }
-                    const float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-                    const int idx = lane >> 1;
-                    const int c = c0 + (idx & 7);
-                    if ((lane & 1) == 0 && c < cend) {
-                        float* a = acc + ((size_t)((idx >> 3) * C + k)) * DS + (c - s0);
-                        *a += tot;
                     }
                 }
+                if (SUMS) {   // stage the chunk channel-major: row = channel, consecutive lanes = consecutive pixels
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) Tw[(c0 - blk + j) * kTRow + 32 * i + lane] = x[i][j];
+                }
+            }
+            if (SUMS) {
+                // ---- class sums of this 32-channel block: lane = channel, walks the tile's 128 pixels in
+                // order keeping a running (sum, sum of squares) for the current class; a class change flushes
+                // into the accumulators this warp alone owns.  Control flow is warp-uniform (every lane sees
+                // the same class sequence) and the summation order is fixed -> deterministic, no atomics.
+                __syncwarp();
+                const int c = blk + lane;
+                if (c < bend) {
+                    const float4* row = reinterpret_cast<const float4*>(Tw + lane * kTRow);
+                    const int4* ys4 = reinterpret_cast<const int4*>(ys);
+                    float* a1 = acc + (c - s0);
+                    float* a2 = acc + (size_t)C * DS + (c - s0);
+                    int cur = -1;
+                    float s1 = 0.f, s2 = 0.f;
+                    auto flush = [&]() {
+                        if (cur >= 0) {
+                            a1[(size_t)cur * DS] += s1;
+                            a2[(size_t)cur * DS] += s2;
+                        }
+                    };
+                    auto one = [&](int yv, float xv) {
+                        if (yv != cur) { flush(); cur = yv; s1 = 0.f; s2 = 0.f; }
+                        s1 += xv;
+                        s2 = fmaf(xv, xv, s2);
+                    };
+#pragma unroll 4
+                    for (int p4 = 0; p4 < kTilePixels / 4; ++p4) {
+                        const int4 yy = ys4[p4];
+                        const float4 v = row[p4];
+                        if (yy.x == cur && yy.y == cur && yy.z == cur && yy.w == cur) {
+                            s1 += (v.x + v.y) + (v.z + v.w);
+                            s2 += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+                        } else {
+                            one(yy.x, v.x); one(yy.y, v.y); one(yy.z, v.z); one(yy.w, v.w);
+                        }
+                    }
+                    flush();
+                }
+                __syncwarp();
             }
         }
 
         if (DIST) {
             // ---- combine the four channel quarters in warp order
+            if (SUMS) __syncthreads();   // the staging area aliases the other warps' transposition tiles
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float* row = dots + ((size_t)warp * kTilePixels + 32 * i + lane) * (CP + 1);
