@@ -128,13 +128,16 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(const float* __res
         for (int w = 0; w < kTableThreads / 32; ++w) v += bias_part[w][tid];
         table[T.off_bias + tid] = (float)v;
     }
-    // TF32 split of -2*Q, class-major, for the tcgen05 kernel (rows >= C are zero)
+    // TF32 split of -2*Q in the tcgen05 B-operand layout (common.cuh); classes >= C are zero rows
     __syncthreads();
-    for (int i = tid; i < 24 * T.Dp; i += kTableThreads) {
-        const int k = i / T.Dp, j = i - k * T.Dp;
+    for (int i = tid; i < 32 * T.Dp; i += kTableThreads) {
+        const int kc = i >> 7, n = (i >> 2) & 31, e = i & 3;
+        const int j = kc * 4 + e;
         float v = 0.f;
-        if (k < T.CP && k < C) v = -2.f * table[T.off_q + (size_t)j * T.CP + k];
-        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+        if (n < C && n < T.CP) v = -2.f * table[T.off_q + (size_t)j * T.CP + n];
+        unsigned hbits;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hbits) : "f"(v));
+        const float hi = __uint_as_float(hbits);
         table[T.off_qhi + i] = hi;
         table[T.off_qlo + i] = v - hi;
     }
@@ -428,7 +431,13 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
     ONDA_REQUIRE(!(labels || soft) || prior, "onda_pseudolabel_fused: labels/soft need a prior");
     ONDA_REQUIRE(impl == ONDA_IMPL_AUTO || impl == ONDA_IMPL_SIMT || impl == ONDA_IMPL_TCGEN05,
                  "onda_pseudolabel_fused: unknown impl %d", impl);
-    ONDA_REQUIRE(impl != ONDA_IMPL_TCGEN05, "onda_pseudolabel_fused: tcgen05 path not built for this shape");
+    const long long n_tiles = ((long long)B * HW + kTilePixels - 1) / kTilePixels;
+    const bool tc_ok = want_dist && tc_supported(B, D, HW, C);
+    ONDA_REQUIRE(impl != ONDA_IMPL_TCGEN05 || tc_ok || !want_dist,
+                 "onda_pseudolabel_fused: the tcgen05 kernel needs distance outputs, D %% 32 == 0, 128 <= D <= 256, C <= 32 "
+                 "(got D=%d C=%d)", D, C);
+    // AUTO: tensor-core kernel when the shape allows and there are enough tiles to fill the machine
+    const bool use_tc = tc_ok && (impl == ONDA_IMPL_TCGEN05 || (impl == ONDA_IMPL_AUTO && n_tiles >= 128));
     const Workspace ws = fused_workspace(B, D, HW, C);
     ONDA_REQUIRE(workspace_bytes >= ws.total, "onda_pseudolabel_fused: workspace too small (%zu < %zu)", workspace_bytes,
                  ws.total);
@@ -447,13 +456,22 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
     p.dots_scratch = (float*)(base + ws.off_dots);
     p.nslices = pl.nslices; p.slice_channels = pl.DS; p.tiles = pl.tiles;
 
-    int rc = launch_fused_simt(p, pl, want_dist, want_sums, stream);
-    if (rc != ONDA_OK) return rc;
-
+    int n_cta, n_stat;
+    if (use_tc) {
+        p.nslices = 1; p.slice_channels = D;
+        n_cta = tc_grid(pl.tiles, sms);
+        n_stat = n_cta;
+        int rc = launch_fused_tc(p, n_cta, want_sums, stream);
+        if (rc != ONDA_OK) return rc;
+    } else {
+        int rc = launch_fused_simt(p, pl, want_dist, want_sums, stream);
+        if (rc != ONDA_OK) return rc;
+        n_cta = pl.grid_x;
+        n_stat = want_dist ? (pl.nslices > 1 ? pl.finish_grid : pl.grid_x) : 0;
+    }
     const int class_elems = 2 * C * D + C;
-    const int n_stat = want_dist ? (pl.nslices > 1 ? pl.finish_grid : pl.grid_x) : 0;
     const int blocks = (class_elems + kStatSlots + 31) / 32;
-    reduce_partials_kernel<<<blocks, 256, 0, stream>>>(p.cta_partials, pl.grid_x, sums_floats(C, D), class_elems,
+    reduce_partials_kernel<<<blocks, 256, 0, stream>>>(p.cta_partials, n_cta, sums_floats(C, D), class_elems,
                                                        want_sums ? 1 : 0, p.stat_partials, n_stat, want_dist ? 1 : 0, sums);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);

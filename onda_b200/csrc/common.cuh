@@ -40,7 +40,9 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 
 // Distance-table layout (floats), built by onda_build_distance_table:
 //   sigma[Dp] | w[Dp] | mu[Dp] | bias[32] | Q[Dp][CP]  (channel-major, CP = padded_classes(C))
-//   | Qhi[CP24][Dp] | Qlo[CP24][Dp]   (class-major TF32 split of -2*Q for the tcgen05 path, CP24 = 24)
+//   | Bhi[Dp/4][32][4] | Blo[Dp/4][32][4]   TF32 split of -2*Q laid out as the tcgen05 B operand:
+//     K-major, no swizzle, 8x16-byte core matrices: element (class n, channel c) sits at float index
+//     (c/4)*128 + n*4 + (c%4), so LBO (next 4 channels) = 512 B and SBO (next 8 classes) = 128 B.
 // Dp = D rounded up to 32; padded channels carry w = 0, Q = 0 so they contribute nothing.
 struct TableLayout {
     int C, D, Dp, CP;
@@ -55,8 +57,8 @@ __host__ __device__ inline TableLayout table_layout(int C, int D) {
     t.off_bias = t.off_mu + t.Dp;
     t.off_q = t.off_bias + 32;
     t.off_qhi = t.off_q + (size_t)t.Dp * t.CP;
-    t.off_qlo = t.off_qhi + (size_t)24 * t.Dp;
-    t.total = t.off_qlo + (size_t)24 * t.Dp;
+    t.off_qlo = t.off_qhi + (size_t)32 * t.Dp;
+    t.total = t.off_qlo + (size_t)32 * t.Dp;
     return t;
 }
 

@@ -34,6 +34,11 @@ struct SimtPlan {
 SimtPlan plan_simt(int B, int D, int HW, int C, int sms, bool dist, bool sums);
 int launch_fused_simt(const FusedParams& p, const SimtPlan& pl, bool dist, bool sums, cudaStream_t stream);
 
+// tcgen05 kernel (fused_tc.cu)
+bool tc_supported(int B, int D, int HW, int C);
+int tc_grid(int tiles, int sms);
+int launch_fused_tc(const FusedParams& p, int grid, bool sums, cudaStream_t stream);
+
 struct PixelStats {
     float proto_conf = 0.f, prior_conf = 0.f, pl_conf = 0.f, entropy = 0.f;
     int pl_pixels = 0, pixels = 0;

@@ -1,0 +1,460 @@
+// tcgen05 implementation of the fused pass for sm_100a (D % 32 == 0, 128 <= D <= 256, C <= 32).
+//
+// Why tensor cores: the CUDA-core kernel (fused_simt.cu) is issue-bound -- 21 FFMA per feature
+// element for the 19-wide contraction alone (profiles/r1_simt_v1_ncu_full.txt) -- so the distance
+// contraction moves to the 5th-generation tensor cores with an error-compensated 3xTF32 split:
+//     x' . Q  =  hi(x').hi(Q) + hi(x').lo(Q) + lo(x').hi(Q)      (fp32 accumulate in TMEM)
+// which keeps fp32-level accuracy (the dropped lo.lo term is 2^-22 relative).
+//
+// One persistent CTA per SM, 25 warps, warp-specialised over a single global chunk sequence
+// (chunk = 128 pixels x 32 channels; a tile of 128 pixels is D/32 consecutive chunks):
+//   warps  0-15  loaders: lane = pixel.  Coalesced 4-byte loads along the NCHW channel planes, then
+//                (a) raw values -> shared-memory transposition tile [channel][pixel] for the class sums,
+//                (b) centred values split into TF32 hi/lo -> TMEM (tcgen05.st) as the A operand
+//                    (lane = pixel, column = channel), (c) sum_j w_j x'_j^2 on the CUDA cores.
+//                Warp w may only touch TMEM lanes 32*(w%4)..+31, so w%4 is the pixel quarter and
+//                w/4 the loader group; group g takes chunks g, g+4, g+8, ...
+//   warp   24    MMA issuer: per chunk 4 K-steps x 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
+//                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory.
+//   warps 16-19  epilogue: tcgen05.ld of the 32 accumulator columns of their pixel, then the common
+//                per-pixel tail (epilogue.cuh): sqrt, softmax, prior rectification, label, statistics.
+//   warps 20-23  class sums: lane = channel walks the 128 pixels of a staged chunk with run-length
+//                accumulation into shared-memory accumulators that the warp alone owns (fixed
+//                summation order, no atomics); also computes the per-pixel class (argmax of logits).
+// Rings: 6 stages of {64 TMEM columns (hi|lo), one 32x132-float smem tile}; 2 accumulator buffers
+// of 32 TMEM columns.  All hand-offs are mbarriers; tcgen05.commit frees A stages / publishes
+// accumulators.
+#include "epilogue.cuh"
+
+namespace onda {
+
+constexpr int kTcLoaderWarps = 16;
+constexpr int kTcEpiWarp0 = 16;
+constexpr int kTcSumWarp0 = 20;
+constexpr int kTcMmaWarp = 24;
+constexpr int kTcThreads = 25 * 32;
+constexpr int kTcStages = 6;
+constexpr int kTcRow = kTilePixels + 4;          // padded row of a staged chunk
+constexpr int kTcChunkC = 32;                    // channels per chunk
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccCol0 = kTcStages * 64;    // accumulators after the A stages
+constexpr long long kSpinLimit = 4000000000LL;   // ~2 s of SM clock: a stuck pipeline traps instead of hanging
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem descriptor]^T, kind::tf32, issued by one thread
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, dense, M x N
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- shared-memory carve-up ------------------------------------------------------------------------
+struct TcSmem {
+    size_t bhi, blo, tiles, acc, out, apart, mu, w, ys, cnt, red, bars, tmem_ptr, total;  // byte offsets
+};
+__host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
+    TcSmem s;
+    size_t o = 0;
+    s.bhi = o; o += (size_t)32 * D * 4;
+    s.blo = o; o += (size_t)32 * D * 4;
+    s.tiles = o; o += sums ? (size_t)kTcStages * kTcChunkC * kTcRow * 4 : 0;
+    s.acc = o; o += sums ? (size_t)2 * C * D * 4 : 0;
+    s.out = o; o += (size_t)kTilePixels * (CP + 1) * 4;
+    s.apart = o; o += (size_t)2 * (D / kTcChunkC) * kTilePixels * 4;
+    s.mu = o; o += (size_t)D * 4;
+    s.w = o; o += (size_t)D * 4;
+    s.ys = o; o += (size_t)2 * kTilePixels * 4;
+    s.cnt = o; o += 32 * 4;
+    s.red = o; o += 4 * kStatSlots * 4;
+    s.bars = o; o += (size_t)(4 * kTcStages + 4) * 8;
+    s.tmem_ptr = o; o += 16;
+    s.total = o;
+    return s;
+}
+
+template <int CP, bool SUMS>
+__global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.C, D = p.D, HW = p.HW;
+    const int NB = D / kTcChunkC;
+    const TcSmem L = tc_smem(D, C, CP, SUMS);
+    float* Bhi = reinterpret_cast<float*>(smem_raw + L.bhi);
+    float* Blo = reinterpret_cast<float*>(smem_raw + L.blo);
+    float* Tst = reinterpret_cast<float*>(smem_raw + L.tiles);
+    float* acc = reinterpret_cast<float*>(smem_raw + L.acc);
+    float* out_stage = reinterpret_cast<float*>(smem_raw + L.out);
+    float* apart = reinterpret_cast<float*>(smem_raw + L.apart);
+    float* mus = reinterpret_cast<float*>(smem_raw + L.mu);
+    float* wsm = reinterpret_cast<float*>(smem_raw + L.w);
+    int* ys = reinterpret_cast<int*>(smem_raw + L.ys);
+    int* cnt = reinterpret_cast<int*>(smem_raw + L.cnt);
+    float* red = reinterpret_cast<float*>(smem_raw + L.red);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.tmem_ptr);
+    const uint32_t bars = smem_u32(smem_raw + L.bars);
+    auto full_a = [&](int s) { return bars + 8u * s; };
+    auto empty_a = [&](int s) { return bars + 8u * (kTcStages + s); };
+    auto full_t = [&](int s) { return bars + 8u * (2 * kTcStages + s); };
+    auto empty_t = [&](int s) { return bars + 8u * (3 * kTcStages + s); };
+    auto acc_full = [&](int i) { return bars + 8u * (4 * kTcStages + i); };
+    auto acc_empty = [&](int i) { return bars + 8u * (4 * kTcStages + 2 + i); };
+
+    const TableLayout T = table_layout(C, D);
+    // ---- one-time setup: tables to shared memory, barriers, tensor memory
+    for (int i = tid; i < 32 * D; i += kTcThreads) {
+        Bhi[i] = p.table[T.off_qhi + i];
+        Blo[i] = p.table[T.off_qlo + i];
+    }
+    for (int i = tid; i < D; i += kTcThreads) {
+        mus[i] = p.table[T.off_mu + i];
+        wsm[i] = p.table[T.off_w + i];
+    }
+    if (SUMS) {
+        for (int i = tid; i < 2 * C * D; i += kTcThreads) acc[i] = 0.f;
+        if (tid < 32) cnt[tid] = 0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; ++s) {
+            mbar_init(full_a(s), 128);
+            mbar_init(empty_a(s), 1);
+            mbar_init(full_t(s), 128);
+            mbar_init(empty_t(s), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(acc_full(i), 1);
+            mbar_init(acc_empty(i), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kTcMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();       // B tables were written through the generic proxy; the tensor core reads them through the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long total_chunks = (long long)my_tiles * NB;
+
+    if (warp < kTcLoaderWarps) {
+        // =========================== loaders ===========================================
+        const int quarter = warp & 3, group = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
+        for (long long q = group; q < total_chunks; q += 4) {
+            const int t = (int)(q / NB), b = (int)(q - (long long)t * NB);
+            const int par = t & 1, stage = (int)(q % kTcStages);
+            const uint32_t use = (uint32_t)(q / kTcStages);
+            const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+            long long n = tile * kTilePixels + 32 * quarter + lane;
+            if (n >= p.N) n = p.N - 1;       // clamp: results of padded rows are never stored (epilogue / ys guard them)
+            const long long bimg = n / HW, pix = n - bimg * HW;
+            const float* src = p.feat + (bimg * D + (long long)b * kTcChunkC) * HW + pix;
+            float x[kTcChunkC];
+#pragma unroll
+            for (int j = 0; j < kTcChunkC; ++j) x[j] = ldg_stream(src + (long long)j * HW);
+
+            if (b == 0 && t >= 2) mbar_wait(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1);   // apart[par] consumed
+            if (SUMS) {
+                mbar_wait(empty_t(stage), (use & 1) ^ 1);
+                float* trow = Tst + (size_t)stage * kTcChunkC * kTcRow + 32 * quarter + lane;
+#pragma unroll
+                for (int j = 0; j < kTcChunkC; ++j) trow[j * kTcRow] = x[j];
+                mbar_arrive(full_t(stage));
+            }
+            mbar_wait(empty_a(stage), (use & 1) ^ 1);
+            tc_fence_after();
+            float a = 0.f;
+            const uint32_t tcol = tmem_base + lane_base + (uint32_t)stage * 64;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = b * kTcChunkC + half * 16 + j;
+                    const float xc = x[half * 16 + j] - mus[c];
+                    a = fmaf(xc * xc, wsm[c], a);
+                    hi[j] = cvt_tf32(xc);
+                    lo[j] = __float_as_uint(xc - __uint_as_float(hi[j]));
+                }
+                tc_st16(tcol + half * 16, hi);
+                tc_st16(tcol + 32 + half * 16, lo);
+            }
+            apart[((size_t)par * NB + b) * kTilePixels + 32 * quarter + lane] = a;
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(full_a(stage));
+        }
+    } else if (warp == kTcMmaWarp) {
+        // =========================== MMA issuer ========================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(128, 32);
+            const uint32_t bhi_addr = smem_u32(Bhi), blo_addr = smem_u32(Blo);
+            for (int t = 0; t < my_tiles; ++t) {
+                const int par = t & 1;
+                if (t >= 2) mbar_wait(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + kAccCol0 + (uint32_t)par * 32;
+                for (int b = 0; b < NB; ++b) {
+                    const long long q = (long long)t * NB + b;
+                    const int stage = (int)(q % kTcStages);
+                    const uint32_t use = (uint32_t)(q / kTcStages);
+                    mbar_wait(full_a(stage), use & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t a_hi = tmem_base + (uint32_t)stage * 64 + ks * 8;
+                        const uint32_t a_lo = a_hi + 32;
+                        const uint32_t koff = (uint32_t)((b * kTcChunkC + ks * 8) / 4) * 512u;   // 4 channels = one 512-byte slab
+                        const uint64_t d_hi = make_bdesc(bhi_addr + koff, 512, 128);
+                        const uint64_t d_lo = make_bdesc(blo_addr + koff, 512, 128);
+                        tc_mma_tf32_ts(dcol, a_hi, d_hi, idesc, (b | ks) != 0);
+                        tc_mma_tf32_ts(dcol, a_hi, d_lo, idesc, 1);
+                        tc_mma_tf32_ts(dcol, a_lo, d_hi, idesc, 1);
+                    }
+                    tc_commit(empty_a(stage));          // A stage reusable once these MMAs retire
+                }
+                tc_commit(acc_full(par));               // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kTcEpiWarp0 && warp < kTcEpiWarp0 + 4) {
+        // =========================== epilogue ===========================================
+        const int et = tid - kTcEpiWarp0 * 32;          // 0..127 = pixel row of the tile = TMEM lane
+        const uint32_t lane_base = (uint32_t)(et & ~31) << 16;
+        PixelStats st;
+        const float* bias = p.table + T.off_bias;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int par = t & 1;
+            const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+            mbar_wait(acc_full(par), ((uint32_t)t >> 1) & 1);
+            tc_fence_after();
+            uint32_t dv[32];
+            tc_ld32(tmem_base + lane_base + kAccCol0 + (uint32_t)par * 32, dv);
+            tc_wait_ld();
+            float a_tot = 0.f;
+            for (int b = 0; b < NB; ++b) a_tot += apart[((size_t)par * NB + b) * kTilePixels + et];
+            tc_fence_before();
+            mbar_arrive(acc_empty(par));
+            float d2[CP];
+#pragma unroll
+            for (int k = 0; k < CP; ++k) d2[k] = (a_tot + __ldg(bias + k)) + __uint_as_float(dv[k]);
+            finish_pixel<CP>(p, d2, tile * kTilePixels, et, out_stage, st);
+        }
+        // fixed-order reduction of the statistics over the four epilogue warps
+        {
+            float v[kStatSlots] = {st.proto_conf, st.prior_conf, st.pl_conf, (float)st.pl_pixels, (float)st.pixels,
+                                   st.entropy, 0.f, 0.f};
+            const int ew = et >> 5;
+#pragma unroll
+            for (int s = 0; s < kStatSlots; ++s) {
+                const float x = warp_sum(v[s]);
+                if (lane == 0) red[ew * kStatSlots + s] = x;
+            }
+            named_bar_sync(2, 128);
+            if (et < kStatSlots) {
+                float x = 0.f;
+                for (int w = 0; w < 4; ++w) x += red[w * kStatSlots + et];
+                p.stat_partials[(size_t)blockIdx.x * kStatSlots + et] = x;
+            }
+        }
+    } else if (SUMS && warp >= kTcSumWarp0 && warp < kTcSumWarp0 + 4) {
+        // =========================== class sums ==========================================
+        const int sw = warp - kTcSumWarp0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int par = t & 1;
+            const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+            int* ysp = ys + par * kTilePixels;
+            {   // class of pixel 32*sw + lane: first argmax of the EMA logits (prototype_handler.py:83-86)
+                const long long n = tile * kTilePixels + 32 * sw + lane;
+                int arg = -1;
+                if (n < p.N) {
+                    const long long bimg = n / HW, pix = n - bimg * HW;
+                    const float* lp = p.logits + (bimg * C) * (long long)HW + pix;
+                    float best = __ldg(lp);
+                    arg = 0;
+                    for (int k = 1; k < C; ++k) {
+                        const float v = __ldg(lp + (long long)k * HW);
+                        if (torch_greater(v, best)) { best = v; arg = k; }
+                    }
+                }
+                ysp[32 * sw + lane] = arg;
+            }
+            named_bar_sync(1, 128);
+            if (sw == 0) {     // pixel counts per class
+                unsigned mask = 0;
+                int y[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    y[i] = ysp[32 * i + lane];
+                    mask |= (y[i] >= 0) ? (1u << y[i]) : 0u;
+                }
+                mask = __reduce_or_sync(0xffffffffu, mask);
+                while (mask) {
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    int c = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c += __popc(__ballot_sync(0xffffffffu, y[i] == k));
+                    if (lane == 0) cnt[k] += c;
+                }
+            }
+            for (int b = sw; b < NB; b += 4) {
+                const long long q = (long long)t * NB + b;
+                const int stage = (int)(q % kTcStages);
+                const uint32_t use = (uint32_t)(q / kTcStages);
+                mbar_wait(full_t(stage), use & 1);
+                const int c = b * kTcChunkC + lane;
+                const float4* row = reinterpret_cast<const float4*>(Tst + ((size_t)stage * kTcChunkC + lane) * kTcRow);
+                const int4* ys4 = reinterpret_cast<const int4*>(ysp);
+                float* a1 = acc + c;
+                float* a2 = acc + (size_t)C * D + c;
+                int cur = -1;
+                float s1 = 0.f, s2 = 0.f;
+                auto flush = [&]() {
+                    if (cur >= 0) {
+                        a1[(size_t)cur * D] += s1;
+                        a2[(size_t)cur * D] += s2;
+                    }
+                };
+                auto one = [&](int yv, float xv) {
+                    if (yv != cur) { flush(); cur = yv; s1 = 0.f; s2 = 0.f; }
+                    s1 += xv;
+                    s2 = fmaf(xv, xv, s2);
+                };
+#pragma unroll 4
+                for (int p4 = 0; p4 < kTilePixels / 4; ++p4) {
+                    const int4 yy = ys4[p4];
+                    const float4 v = row[p4];
+                    if (yy.x == cur && yy.y == cur && yy.z == cur && yy.w == cur) {
+                        s1 += (v.x + v.y) + (v.z + v.w);
+                        s2 += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+                    } else {
+                        one(yy.x, v.x); one(yy.y, v.y); one(yy.z, v.z); one(yy.w, v.w);
+                    }
+                }
+                flush();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_t(stage));
+            }
+        }
+    }
+
+    // ---- teardown: publish the class partials, release tensor memory
+    tc_fence_before();
+    __syncthreads();
+    if (SUMS) {
+        float* out = p.cta_partials + (size_t)blockIdx.x * sums_floats(C, D);
+        for (int i = tid; i < 2 * C * D; i += kTcThreads) out[i] = acc[i];
+        if (tid < C) out[(size_t)2 * C * D + tid] = (float)cnt[tid];
+    }
+    if (warp == kTcMmaWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+bool tc_supported(int B, int D, int HW, int C) {
+    (void)B; (void)HW;
+    return D % 32 == 0 && D >= 128 && D <= 256 && C >= 1 && C <= 32;
+}
+
+int tc_grid(int tiles, int sms) { return tiles < sms ? tiles : sms; }
+
+template <int CP, bool SUMS>
+static int launch_tc(const FusedParams& p, int grid, cudaStream_t stream) {
+    auto kern = fused_tc_kernel<CP, SUMS>;
+    const size_t smem = tc_smem(p.D, p.C, CP, SUMS).total;
+    ONDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    timing_begin(stream);
+    kern<<<grid, kTcThreads, smem, stream>>>(p);
+    timing_end(stream);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int launch_fused_tc(const FusedParams& p, int grid, bool sums, cudaStream_t stream) {
+    const int CP = padded_classes(p.C);
+    if (CP == 20) return sums ? launch_tc<20, true>(p, grid, stream) : launch_tc<20, false>(p, grid, stream);
+    return sums ? launch_tc<32, true>(p, grid, stream) : launch_tc<32, false>(p, grid, stream);
+}
+
+}  // namespace onda

@@ -21,7 +21,13 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 OPS = sorted(glob.glob(os.path.join(GOLDEN, "ops_*.npz")))
-IMPLS = ["simt"]
+IMPLS = ["simt", "tcgen05"]
+
+
+def need_shape(impl, D, C=19):
+    """The tcgen05 kernel covers D % 32 == 0, 128 <= D <= 256, C <= 32; everything else is the CUDA-core kernel."""
+    if impl == "tcgen05" and not (D % 32 == 0 and 128 <= D <= 256 and C <= 32):
+        pytest.skip(f"tcgen05 kernel does not cover D={D}, C={C}")
 
 
 def dev():
@@ -82,6 +88,7 @@ def close_rel_max(got, ref, tol=1e-5):
 def test_golden_ops(path, impl):
     from onda_b200 import Monitor
     z = np.load(path)
+    need_shape(impl, z["protos"].shape[1])
     metric, tau, thresh, lam = str(z["metric"]), float(z["tau"]), float(z["thresh"]), float(z["ma_lambda"])
     protos, sq_mean, counter = T(z["protos"]), T(z["sq_mean"]), T(z["counter"])
     h = make_handler(protos, sq_mean, counter, metric, tau, thresh, lam, impl)
@@ -120,7 +127,7 @@ def test_golden_ops(path, impl):
 
 @pytest.mark.parametrize("impl", IMPLS)
 def test_fused_equals_separate_calls(impl):
-    case = po.synth_case(21, 2, 64, 11, 19)
+    case = po.synth_case(21, 2, 128, 11, 19)
     hs = [make_handler(case["protos"], case["sq_mean"], case["counter"], "mahalanobis", impl=impl, fuse_hard_soft=f)
           for f in (True, False)]
     feat, prior, out = (case[k].to(dev()) for k in ("feat", "prior", "out"))
@@ -178,12 +185,17 @@ SHAPES = [
     (37, 1, 64, 17, 9, 25, "mahalanobis"),        # more than 20 classes (32-wide path)
     (38, 5, 24, 1, 1, 19, "euclidean"),           # 5 pixels in total
     (39, 2, 320, 3, 51, 19, "mahalanobis"),       # HW = 153
+    (40, 2, 128, 21, 13, 19, "mahalanobis"),      # tcgen05 range: D = 128, ragged last tile
+    (42, 3, 192, 5, 31, 7, "euclidean"),          # D = 192 (6 chunks), few classes
+    (43, 1, 256, 9, 14, 25, "mahalanobis"),       # 25 classes (32-wide epilogue), 126 pixels: a single partial tile
+    (44, 7, 160, 37, 53, 19, "mahalanobis"),      # D = 160 (5 chunks), 13727 pixels
 ]
 
 
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("seed,B,D,h,w,C,metric", SHAPES)
 def test_oracle_parity_shapes(seed, B, D, h, w, C, metric, impl):
+    need_shape(impl, D, C)
     case = po.synth_case(seed, B, D, h, w, c=C)
     hd = make_handler(case["protos"], case["sq_mean"], case["counter"], metric, impl=impl)
     orc = make_oracle(case["protos"], case["sq_mean"], case["counter"], metric)
@@ -225,6 +237,7 @@ def test_sequence_of_steps_golden(impl):
     from onda_b200 import Monitor
     z = np.load(os.path.join(GOLDEN, "sequence_ma.npz"))
     steps, d = int(z["steps"]), int(z["d"])
+    need_shape(impl, d)
     first = po.synth_case(4999, 1, d, 9, 11)
     h = make_handler(first["protos"], first["sq_mean"], first["counter"], "mahalanobis", ma_lambda=0.95, impl=impl)
     mon = Monitor(50, 0.003, "hamming")
@@ -327,6 +340,7 @@ def check_labels_loose(labels, ref_labels, ref_soft, thresh, margin=1e-4):
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("B,D,h,w", [(32, 256, 65, 129), (8, 256, 129, 257), (8, 2048, 65, 129)])
 def test_full_size_properties(B, D, h, w, impl):
+    need_shape(impl, D)
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + D)
     d = dev()
     C = 19
