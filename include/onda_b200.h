@@ -44,7 +44,7 @@ extern "C" {
 /* kernel selection for onda_pseudolabel_fused (ONDA_IMPL_AUTO picks tcgen05 when the shape allows) */
 #define ONDA_IMPL_AUTO 0
 #define ONDA_IMPL_SIMT 1    /* CUDA-core kernel, any shape */
-#define ONDA_IMPL_TCGEN05 2 /* 3xTF32 tcgen05.mma kernel, D % 32 == 0, D <= 512, C <= 24 */
+#define ONDA_IMPL_TCGEN05 2 /* 3xTF32 tcgen05.mma kernel: D = 128 or 256, C <= 32 (see onda_impl_supported) */
 
 /* Number of statistic slots at the tail of a `sums` buffer (see onda_sums_floats). */
 #define ONDA_NUM_STATS 8
@@ -72,6 +72,10 @@ unsigned long long onda_launch_count(void);
 int onda_kernel_timing_enable(int enable);
 int onda_kernel_timing_read(float* total_ms_host, int* launches_host);
 
+/* Diagnostics: when a device buffer of gridDim*32*8 int64 is set, the tcgen05 kernel records per-warp cycle
+ * counters (time spent in each pipeline wait, total) into it.  NULL (default) disables it. */
+int onda_debug_set_buffer(void* device_buffer);
+
 /* ---- buffer sizing (host, no CUDA calls) ----------------------------------- */
 /* floats in a distance table built by onda_build_distance_table */
 size_t onda_table_floats(int C, int D);
@@ -79,6 +83,9 @@ size_t onda_table_floats(int C, int D);
 size_t onda_sums_floats(int C, int D);
 /* bytes of scratch onda_pseudolabel_fused needs for this shape (per-CTA partials, split-D dots) */
 size_t onda_fused_workspace_bytes(int B, int D, int HW, int C, int impl);
+
+/* 1 if `impl` (ONDA_IMPL_SIMT / ONDA_IMPL_TCGEN05) has a kernel for this shape, else 0 (host only) */
+int onda_impl_supported(int B, int D, int HW, int C, int impl);
 
 /* ---- prototype statistics ------------------------------------------------- */
 /*

@@ -26,10 +26,12 @@ _SIGNATURES = {
     "onda_last_error": (C.c_char_p, []),
     "onda_sm_count": (C.c_int, []),
     "onda_launch_count": (C.c_ulonglong, []),
+    "onda_debug_set_buffer": (C.c_int, [_p]),
     "onda_kernel_timing_enable": (C.c_int, [C.c_int]),
     "onda_kernel_timing_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "onda_table_floats": (C.c_size_t, [C.c_int, C.c_int]),
     "onda_sums_floats": (C.c_size_t, [C.c_int, C.c_int]),
+    "onda_impl_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "onda_fused_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "onda_build_distance_table": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "onda_table_global_std": (C.c_int, [_p, C.c_int, C.c_int, _p, _p]),

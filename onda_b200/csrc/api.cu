@@ -332,6 +332,12 @@ int onda_sm_count(void) {
 
 unsigned long long onda_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
+static long long* g_debug = nullptr;
+int onda_debug_set_buffer(void* device_buffer) {
+    g_debug = (long long*)device_buffer;
+    return ONDA_OK;
+}
+
 int onda_kernel_timing_enable(int enable) {
     g_timing = enable != 0;
     g_timed = 0;
@@ -376,6 +382,12 @@ static Workspace fused_workspace(int B, int D, int HW, int C) {
     const size_t dots = pl.nslices > 1 ? (size_t)pl.nslices * (padded_classes(C) + 1) * (size_t)B * HW * sizeof(float) : 0;
     w.total = align256(w.off_dots + dots);
     return w;
+}
+
+int onda_impl_supported(int B, int D, int HW, int C, int impl) {
+    if (B <= 0 || D <= 0 || HW <= 0 || C <= 0 || C > ONDA_MAX_CLASSES) return 0;
+    if (impl == ONDA_IMPL_TCGEN05) return tc_supported(B, D, HW, C) ? 1 : 0;
+    return (impl == ONDA_IMPL_SIMT || impl == ONDA_IMPL_AUTO) ? 1 : 0;
 }
 
 size_t onda_fused_workspace_bytes(int B, int D, int HW, int C, int impl) {
@@ -434,7 +446,7 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
     const long long n_tiles = ((long long)B * HW + kTilePixels - 1) / kTilePixels;
     const bool tc_ok = want_dist && tc_supported(B, D, HW, C);
     ONDA_REQUIRE(impl != ONDA_IMPL_TCGEN05 || tc_ok || !want_dist,
-                 "onda_pseudolabel_fused: the tcgen05 kernel needs distance outputs, D %% 32 == 0, 128 <= D <= 256, C <= 32 "
+                 "onda_pseudolabel_fused: the tcgen05 kernel covers D = 128 or 256 and C <= 32 "
                  "(got D=%d C=%d)", D, C);
     // AUTO: tensor-core kernel when the shape allows and there are enough tiles to fill the machine
     const bool use_tc = tc_ok && (impl == ONDA_IMPL_TCGEN05 || (impl == ONDA_IMPL_AUTO && n_tiles >= 128));
@@ -448,13 +460,14 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
     memset(&p, 0, sizeof(p));
     p.feat = feat; p.prior = prior; p.logits = logits; p.table = table;
     p.B = B; p.D = D; p.HW = HW; p.C = C; p.N = (long long)B * HW;
-    p.tau = tau; p.thresh = thresh;
+    p.tau = tau; p.inv_tau = 1.0f / tau; p.thresh = thresh;
     p.labels = (long long*)labels; p.soft = soft; p.dist = dist;
     char* base = (char*)workspace;
     p.cta_partials = (float*)(base + ws.off_cta);
     p.stat_partials = (float*)(base + ws.off_stat);
     p.dots_scratch = (float*)(base + ws.off_dots);
     p.nslices = pl.nslices; p.slice_channels = pl.DS; p.tiles = pl.tiles;
+    p.debug = g_debug;
 
     int n_cta, n_stat;
     if (use_tc) {

@@ -14,7 +14,7 @@ struct FusedParams {
     const float* table;    // distance table (common.cuh: TableLayout)
     int B, D, HW, C;
     long long N;           // B * HW
-    float tau, thresh;
+    float tau, inv_tau, thresh;   // inv_tau = 1/tau computed on the host
     long long* labels;     // [N] or null
     float* soft;           // [N][C] or null
     float* dist;           // [N][C] or null
@@ -24,6 +24,7 @@ struct FusedParams {
     int nslices;           // channel slices (gridDim.y)
     int slice_channels;    // channels per slice, multiple of 32
     int tiles;             // ceil(N / 128)
+    long long* debug;      // optional [gridDim.x][32 warps][8] cycle counters (onda_debug_set_buffer), else null
 };
 
 // launch plan of the CUDA-core kernel (fused_simt.cu)
@@ -44,76 +45,105 @@ struct PixelStats {
     int pl_pixels = 0, pixels = 0;
 };
 
+// Loads the C logits of pixel n (NCHW, coalesced across a warp) with every load in flight at once.
+template <int CP>
+__device__ __forceinline__ void load_pixel_row(const float* base, int C, int HW, long long n, float (&v)[CP]) {
+    const long long b = n / HW, q = n - b * HW;
+    const float* lp = base + (b * C) * (long long)HW + q;
+#pragma unroll
+    for (int k = 0; k < CP; ++k) v[k] = (k < C) ? __ldg(lp + (long long)k * HW) : 0.f;
+}
+
+// First maximal index with torch semantics (prototype_handler.onehot, prototype_handler.py:83-86).
+template <int CP>
+__device__ __forceinline__ int first_argmax(const float (&v)[CP], int C) {
+    float best = v[0];
+    int arg = 0;
+#pragma unroll
+    for (int k = 1; k < CP; ++k)
+        if (k < C && torch_greater(v[k], best)) { best = v[k]; arg = k; }
+    return arg;
+}
+
+// ---- fast single-instruction math (MUFU): relative error ~2^-22, far inside the 1e-5 parity budget
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // Everything after the squared distances for one pixel (one thread).  Follows
 // prototype_handler.pseudo_labels (prototype_handler.py:140-166) step by step:
 //   d' = d - min d (:124-125) ; q = softmax(-d'/tau) (:147) ; stat max q (:150) ;
 //   r = q*prior ; r /= sum r (:159-160) ; (m, l) = max r ; l = 255 if m < thresh (:163-166)
-// with torch's first-index / NaN-first max semantics.  d2 holds squared distances on entry;
-// on exit r[] holds the rectified posterior and dsh[] the shifted distances.
-template <int CP>
-__device__ __forceinline__ void rectify_pixel(const float (&d2)[CP], const float (&pri)[CP], int C, float tau,
-                                              float thresh, bool have_prior, float (&r)[CP], float (&dsh)[CP],
-                                              int& label, float& m_out, float& maxq, float& maxprior,
-                                              float& entropy) {
-    float dmin = __int_as_float(0x7f800000);
+// with torch's first-index max and NaN behaviour (a NaN row keeps label 0: `nan < thresh` is false).
+// The divisions by the (row-constant) softmax and renormalisation sums are reciprocal multiplies.
+// On entry v[] holds squared distances; on exit v[] holds the rectified posterior r (WANT_DIST:
+// dsh[] additionally receives the shifted distances).
+template <int CP, bool WANT_DIST>
+__device__ __forceinline__ void rectify_pixel(float (&v)[CP], const float (&pri)[CP], int C, float inv_tau, float thresh,
+                                              bool have_prior, float (&dsh)[WANT_DIST ? CP : 1], int& label,
+                                              float& m_out, float& maxq, float& maxprior, float& entropy) {
+    const float inf = __int_as_float(0x7f800000);
+    float dmin = inf, dmax = 0.f;
 #pragma unroll
     for (int k = 0; k < CP; ++k) {
         if (k < C) {
-            float v = d2[k];
-            v = v < 0.f ? 0.f : v;  // keeps NaN (a negative pooled variance gives NaN like the reference)
-            float d = sqrtf(v);
-            dsh[k] = d;
-            if (d < dmin || d != d) dmin = d;
+            float x = v[k];
+            x = x < 0.f ? 0.f : x;              // rounding can make a ~0 squared distance negative; keeps NaN
+            const float d = fast_sqrt(x);
+            v[k] = d;
+            dmin = (d < dmin || d != d) ? d : dmin;
+            dmax = fmaxf(dmax, d);
         }
     }
-    float zmax = -__int_as_float(0x7f800000);
+    // softmax(-d'/tau) = 2^((d' - ref) * scale) / sum, ref = the d' whose exponent is the row maximum:
+    // 0 for tau > 0 (the usual case), max d' for a negative tau
+    const float scale = -1.4426950408889634f * inv_tau;
+    const float ref = inv_tau > 0.f ? 0.f : dmax - dmin;
+    float esum = 0.f, emax = 0.f;
 #pragma unroll
     for (int k = 0; k < CP; ++k) {
         if (k < C) {
-            dsh[k] = dsh[k] - dmin;
-            float z = __fdiv_rn(-dsh[k], tau);
-            r[k] = z;
-            if (z > zmax || z != z) zmax = z;
-        }
-    }
-    float esum = 0.f;
-#pragma unroll
-    for (int k = 0; k < CP; ++k) {
-        if (k < C) {
-            float e = exp2f((r[k] - zmax) * 1.4426950408889634f);
-            r[k] = e;
+            const float ds = v[k] - dmin;
+            if (WANT_DIST) dsh[k] = ds;
+            const float e = fast_ex2((ds - ref) * scale);
+            v[k] = e;
             esum += e;
+            emax = fmaxf(emax, e);
         }
     }
-    maxq = -1.f;
-    maxprior = -__int_as_float(0x7f800000);
+    const float inv_e = fast_rcp(esum);
+    maxq = emax * inv_e;
+    if (esum != esum) maxq = esum;                         // NaN row
+    maxprior = -inf;
     float rsum = 0.f;
 #pragma unroll
     for (int k = 0; k < CP; ++k) {
         if (k < C) {
-            float q = __fdiv_rn(r[k], esum);
-            if (torch_greater(q, maxq)) maxq = q;
+            float q = v[k] * inv_e;
             if (have_prior) {
-                if (torch_greater(pri[k], maxprior)) maxprior = pri[k];
+                maxprior = fmaxf(maxprior, pri[k]);
                 q = q * pri[k];
             }
-            r[k] = q;
+            v[k] = q;
             rsum += q;
         }
     }
-    float best = -__int_as_float(0x7f800000);
+    const float inv_r = have_prior ? fast_rcp(rsum) : 1.f;
+    float best = -inf;
     int arg = 0;
     entropy = 0.f;
-    const float inv_log2c = 1.f / log2f((float)C);
 #pragma unroll
     for (int k = 0; k < CP; ++k) {
         if (k < C) {
-            float v = have_prior ? __fdiv_rn(r[k], rsum) : r[k];
-            r[k] = v;
-            if (torch_greater(v, best)) { best = v; arg = k; }
-            entropy -= v * log2f(v + 1e-30f) * inv_log2c;
+            const float r = v[k] * inv_r;
+            v[k] = r;
+            if (r > best) { best = r; arg = k; }
+            entropy = fmaf(r, fast_lg2(r + 1e-30f), entropy);
         }
     }
+    entropy = -entropy / log2f((float)C);
+    if (rsum != rsum) { best = rsum; arg = 0; }            // torch.max on a NaN row: value NaN, first index
     m_out = best;
     label = (best < thresh) ? ONDA_IGNORE_LABEL : arg;
 }
@@ -135,28 +165,29 @@ __device__ __forceinline__ void warp_copy_rows(const float* stage_rows, float* g
 
 // Tail for one tile row handled by thread `t` (pixel n = tile_base + t).  `stage` is a
 // [128][CP+1] shared-memory slab; rows 32*warp .. 32*warp+31 belong to this warp.
-template <int CP>
-__device__ __forceinline__ void finish_pixel(const FusedParams& p, const float (&d2)[CP], long long tile_base, int t,
-                                             float* stage, PixelStats& st) {
+template <int CP, bool WANT_DIST>
+__device__ __forceinline__ void finish_pixel(const FusedParams& p, float (&d2)[CP], long long tile_base, int t,
+                                             float* stage, PixelStats& st, const float* preloaded_prior = nullptr) {
     const int lane = t & 31, warp = t >> 5;
     const long long n = tile_base + t;
     const bool valid = n < p.N;
     const bool want_post = (p.labels != nullptr) || (p.soft != nullptr);
-    float pri[CP], r[CP], dsh[CP];
+    float pri[CP];
+    float dsh[WANT_DIST ? CP : 1];
     const bool have_prior = p.prior != nullptr;
-    if (valid && have_prior && want_post) {
-        const long long b = n / p.HW;
-        const long long q = n - b * p.HW;
-        const float* pp = p.prior + (b * p.C) * (long long)p.HW + q;
+    if (preloaded_prior != nullptr) {
 #pragma unroll
-        for (int k = 0; k < CP; ++k) pri[k] = (k < p.C) ? __ldg(pp + (long long)k * p.HW) : 0.f;
+        for (int k = 0; k < CP; ++k) pri[k] = preloaded_prior[k];
+    } else if (valid && have_prior && want_post) {
+        load_pixel_row<CP>(p.prior, p.C, p.HW, n, pri);
     } else {
 #pragma unroll
         for (int k = 0; k < CP; ++k) pri[k] = 0.f;
     }
     int label = 0;
     float m = 0.f, maxq = 0.f, maxprior = 0.f, ent = 0.f;
-    rectify_pixel<CP>(d2, pri, p.C, p.tau, p.thresh, have_prior && want_post, r, dsh, label, m, maxq, maxprior, ent);
+    rectify_pixel<CP, WANT_DIST>(d2, pri, p.C, p.inv_tau, p.thresh, have_prior && want_post, dsh, label, m, maxq,
+                                 maxprior, ent);
     if (valid) {
         st.proto_conf += maxq;
         st.pixels += 1;
@@ -176,11 +207,11 @@ __device__ __forceinline__ void finish_pixel(const FusedParams& p, const float (
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CP; ++k)
-            if (k < p.C) stage[t * (CP + 1) + k] = r[k];
+            if (k < p.C) stage[t * (CP + 1) + k] = d2[k];
         __syncwarp();
         warp_copy_rows<CP>(my_rows, p.soft + warp_base * p.C, rows, p.C, lane);
     }
-    if (p.dist != nullptr) {
+    if (WANT_DIST && p.dist != nullptr) {
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CP; ++k)

@@ -89,14 +89,9 @@ __global__ void __launch_bounds__(kSimtThreads, 2) fused_simt_kernel(const Fused
             const long long n = tile_base + tid;
             int arg = -1;
             if (n < p.N) {
-                const long long b = n / HW, q = n - b * HW;
-                const float* lp = p.logits + (b * C) * (long long)HW + q;
-                float best = __ldg(lp);
-                arg = 0;
-                for (int k = 1; k < C; ++k) {
-                    float v = __ldg(lp + (long long)k * HW);
-                    if (torch_greater(v, best)) { best = v; arg = k; }
-                }
+                float lv[CP];
+                load_pixel_row<CP>(p.logits, C, HW, n, lv);
+                arg = first_argmax<CP>(lv, C);
             }
             ys[tid] = arg;
         }
@@ -260,7 +255,8 @@ __global__ void __launch_bounds__(kSimtThreads, 2) fused_simt_kernel(const Fused
                 const float* bias = p.table + T.off_bias;
 #pragma unroll
                 for (int k = 0; k < CP; ++k) d2[k] = fmaf(-2.f, d2[k], a_tot + __ldg(bias + k));
-                finish_pixel<CP>(p, d2, tile_base, tid, dots, st);
+                if (p.dist != nullptr) finish_pixel<CP, true>(p, d2, tile_base, tid, dots, st);
+                else finish_pixel<CP, false>(p, d2, tile_base, tid, dots, st);
             } else {
                 const long long n = tile_base + tid;
                 if (n < p.N) {
@@ -318,7 +314,8 @@ __global__ void __launch_bounds__(kSimtThreads) split_finish_kernel(const FusedP
 #pragma unroll
         for (int k = 0; k < CP; ++k) d2[k] = fmaf(-2.f, d2[k], a_tot + __ldg(bias + k));
         __syncthreads();
-        finish_pixel<CP>(p, d2, tile_base, tid, stage, st);
+        if (p.dist != nullptr) finish_pixel<CP, true>(p, d2, tile_base, tid, stage, st);
+        else finish_pixel<CP, false>(p, d2, tile_base, tid, stage, st);
     }
     __syncthreads();
     write_stat_partial(st, red, p.stat_partials + (size_t)blockIdx.x * kStatSlots, kSimtThreads / 32);

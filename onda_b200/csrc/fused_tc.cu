@@ -1,4 +1,4 @@
-// tcgen05 implementation of the fused pass for sm_100a (D % 32 == 0, 128 <= D <= 256, C <= 32).
+// tcgen05 implementation of the fused pass for sm_100a (D = 128 or 256, C <= 32).
 //
 // Why tensor cores: the CUDA-core kernel (fused_simt.cu) is issue-bound -- 21 FFMA per feature
 // element for the 19-wide contraction alone (profiles/r1_simt_v1_ncu_full.txt) -- so the distance
@@ -21,9 +21,11 @@
 //   warps 20-23  class sums: lane = channel walks the 128 pixels of a staged chunk with run-length
 //                accumulation into shared-memory accumulators that the warp alone owns (fixed
 //                summation order, no atomics); also computes the per-pixel class (argmax of logits).
-// Rings: 6 stages of {64 TMEM columns (hi|lo), one 32x132-float smem tile}; 2 accumulator buffers
-// of 32 TMEM columns.  All hand-offs are mbarriers; tcgen05.commit frees A stages / publishes
-// accumulators.
+// Stages: one {64 TMEM columns (hi|lo), 32x132-float smem tile} pair per loader group, so every
+// mbarrier has exactly one producer side and one consumer side that visit it in order (a parity
+// wait is never more than one phase away from the barrier); class-sum warp s consumes the tiles of
+// loader group s, which with D/32 a multiple of 4 is always the same set of channel blocks.
+// Two accumulator buffers of 32 TMEM columns.  tcgen05.commit frees A stages / publishes accumulators.
 #include "epilogue.cuh"
 
 namespace onda {
@@ -33,12 +35,12 @@ constexpr int kTcEpiWarp0 = 16;
 constexpr int kTcSumWarp0 = 20;
 constexpr int kTcMmaWarp = 24;
 constexpr int kTcThreads = 25 * 32;
-constexpr int kTcStages = 6;
-constexpr int kTcRow = kTilePixels + 4;          // padded row of a staged chunk
+constexpr int kTcStages = 4;                     // = loader groups
+constexpr int kTcRow = kTilePixels + 5;          // padded (odd) row of a staged chunk: lane = channel reads any pixel column conflict-free
 constexpr int kTcChunkC = 32;                    // channels per chunk
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = kTcStages * 64;    // accumulators after the A stages
-constexpr long long kSpinLimit = 4000000000LL;   // ~2 s of SM clock: a stuck pipeline traps instead of hanging
+constexpr uint32_t kSpinLimit = 20000000u;       // failed probes (each followed by a <=256 ns sleep) before giving up
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -49,6 +51,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One non-blocking probe of an mbarrier phase.
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -58,12 +61,23 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// Wait with exponential back-off: up to ~20 of the 25 warps of the CTA are waiting at any moment, and
+// tight polling floods the shared-memory pipeline that the working warps need for LDS/STS.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t ns = 32, tries = 0;
     while (!mbar_try(bar, parity)) {
-        if (clock64() - t0 > kSpinLimit) __trap();
+        __nanosleep(ns);
+        if (ns < 256) ns <<= 1;
+        if (++tries > kSpinLimit) __trap();   // a stuck pipeline traps instead of hanging the GPU
     }
+}
+// wait that adds its duration to a diagnostic counter when profiling is on
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, long long& acc_cycles) {
+    if (!prof) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc_cycles += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -124,7 +138,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------
 struct TcSmem {
-    size_t bhi, blo, tiles, acc, out, apart, mu, w, ys, cnt, red, bars, tmem_ptr, total;  // byte offsets
+    size_t bhi, blo, tiles, acc, out, apart, mu, w, perm, scls, wc, cnt, red, bars, tmem_ptr, total;  // byte offsets
 };
 __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     TcSmem s;
@@ -137,7 +151,9 @@ __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     s.apart = o; o += (size_t)2 * (D / kTcChunkC) * kTilePixels * 4;
     s.mu = o; o += (size_t)D * 4;
     s.w = o; o += (size_t)D * 4;
-    s.ys = o; o += (size_t)2 * kTilePixels * 4;
+    s.perm = o; o += (size_t)2 * kTilePixels * 4;      // class-sorted order -> pixel of the tile (per tile parity)
+    s.scls = o; o += (size_t)2 * kTilePixels * 4;      // class of each sorted entry (-1 = padding pixel)
+    s.wc = o; o += (size_t)2 * 4 * 36 * 4;             // per-warp class histograms
     s.cnt = o; o += 32 * 4;
     s.red = o; o += 4 * kStatSlots * 4;
     s.bars = o; o += (size_t)(4 * kTcStages + 4) * 8;
@@ -146,7 +162,7 @@ __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     return s;
 }
 
-template <int CP, bool SUMS>
+template <int CP, bool SUMS, bool WANT_DIST>
 __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,7 +177,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     float* apart = reinterpret_cast<float*>(smem_raw + L.apart);
     float* mus = reinterpret_cast<float*>(smem_raw + L.mu);
     float* wsm = reinterpret_cast<float*>(smem_raw + L.w);
-    int* ys = reinterpret_cast<int*>(smem_raw + L.ys);
+    int* perm = reinterpret_cast<int*>(smem_raw + L.perm);
+    int* scls = reinterpret_cast<int*>(smem_raw + L.scls);
+    int* wcnt = reinterpret_cast<int*>(smem_raw + L.wc);
     int* cnt = reinterpret_cast<int*>(smem_raw + L.cnt);
     float* red = reinterpret_cast<float*>(smem_raw + L.red);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.tmem_ptr);
@@ -210,6 +228,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    const bool prof = p.debug != nullptr;
+    long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_start = clock64();
     const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const long long total_chunks = (long long)my_tiles * NB;
 
@@ -219,8 +240,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
         for (long long q = group; q < total_chunks; q += 4) {
             const int t = (int)(q / NB), b = (int)(q - (long long)t * NB);
-            const int par = t & 1, stage = (int)(q % kTcStages);
-            const uint32_t use = (uint32_t)(q / kTcStages);
+            const int par = t & 1, stage = group;
+            const uint32_t use = (uint32_t)(q >> 2);
             const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
             long long n = tile * kTilePixels + 32 * quarter + lane;
             if (n >= p.N) n = p.N - 1;       // clamp: results of padded rows are never stored (epilogue / ys guard them)
@@ -229,16 +250,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             float x[kTcChunkC];
 #pragma unroll
             for (int j = 0; j < kTcChunkC; ++j) x[j] = ldg_stream(src + (long long)j * HW);
+            if (prof) {   // time until the last of the 32 loads has landed
+                const long long t0 = clock64();
+                uint32_t sink;
+                asm volatile("mov.b32 %0, %1;" : "=r"(sink) : "f"(x[kTcChunkC - 1]));
+                dbg[3] += clock64() - t0 + (sink == 0x7fc12345u ? 1 : 0);
+            }
 
-            if (b == 0 && t >= 2) mbar_wait(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1);   // apart[par] consumed
+            if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // apart[par] of tile t-2 consumed
             if (SUMS) {
-                mbar_wait(empty_t(stage), (use & 1) ^ 1);
+                mbar_wait_t(empty_t(stage), (use & 1) ^ 1, prof, dbg[1]);
                 float* trow = Tst + (size_t)stage * kTcChunkC * kTcRow + 32 * quarter + lane;
 #pragma unroll
                 for (int j = 0; j < kTcChunkC; ++j) trow[j * kTcRow] = x[j];
                 mbar_arrive(full_t(stage));
             }
-            mbar_wait(empty_a(stage), (use & 1) ^ 1);
+            mbar_wait_t(empty_a(stage), (use & 1) ^ 1, prof, dbg[2]);
             tc_fence_after();
             float a = 0.f;
             const uint32_t tcol = tmem_base + lane_base + (uint32_t)stage * 64;
@@ -268,14 +295,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const uint32_t bhi_addr = smem_u32(Bhi), blo_addr = smem_u32(Blo);
             for (int t = 0; t < my_tiles; ++t) {
                 const int par = t & 1;
-                if (t >= 2) mbar_wait(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1);
+                if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + kAccCol0 + (uint32_t)par * 32;
                 for (int b = 0; b < NB; ++b) {
                     const long long q = (long long)t * NB + b;
-                    const int stage = (int)(q % kTcStages);
-                    const uint32_t use = (uint32_t)(q / kTcStages);
-                    mbar_wait(full_a(stage), use & 1);
+                    const int stage = (int)(q & 3);
+                    const uint32_t use = (uint32_t)(q >> 2);
+                    mbar_wait_t(full_a(stage), use & 1, prof, dbg[1]);
                     tc_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
@@ -303,7 +330,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         for (int t = 0; t < my_tiles; ++t) {
             const int par = t & 1;
             const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-            mbar_wait(acc_full(par), ((uint32_t)t >> 1) & 1);
+            float pri[CP];
+            {   // prior row of this pixel: issued before the wait so its latency hides behind the MMAs
+                const long long n = tile * kTilePixels + et;
+                if (n < p.N && p.prior != nullptr && (p.labels != nullptr || p.soft != nullptr)) {
+                    load_pixel_row<CP>(p.prior, C, HW, n, pri);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CP; ++k) pri[k] = 0.f;
+                }
+            }
+            mbar_wait_t(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
             tc_fence_after();
             uint32_t dv[32];
             tc_ld32(tmem_base + lane_base + kAccCol0 + (uint32_t)par * 32, dv);
@@ -315,7 +352,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             float d2[CP];
 #pragma unroll
             for (int k = 0; k < CP; ++k) d2[k] = (a_tot + __ldg(bias + k)) + __uint_as_float(dv[k]);
-            finish_pixel<CP>(p, d2, tile * kTilePixels, et, out_stage, st);
+            finish_pixel<CP, WANT_DIST>(p, d2, tile * kTilePixels, et, out_stage, st, pri);
         }
         // fixed-order reduction of the statistics over the four epilogue warps
         {
@@ -336,80 +373,103 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         }
     } else if (SUMS && warp >= kTcSumWarp0 && warp < kTcSumWarp0 + 4) {
         // =========================== class sums ==========================================
+        // Per tile the four warps first sort the 128 pixels by class (stable counting sort; class = first
+        // argmax of the EMA logits, prototype_handler.py:83-86).  Each staged chunk is then summed in that
+        // order: lane = channel, one running (sum, sum of squares) per class, at most one accumulator
+        // update per class and chunk -- the cost does not depend on how noisy the class map is, the
+        // summation order is fixed, and every accumulator has a single owner (no atomics).
         const int sw = warp - kTcSumWarp0;
+        float lv[CP];
+        auto fetch_logits = [&](int t) {   // the logits of tile t+1 are fetched while tile t is being summed
+            const long long n = ((long long)blockIdx.x + (long long)t * gridDim.x) * kTilePixels + 32 * sw + lane;
+            if (t < my_tiles && n < p.N) load_pixel_row<CP>(p.logits, C, HW, n, lv);
+        };
+        fetch_logits(0);
+        const unsigned lt_mask = (1u << lane) - 1u;
         for (int t = 0; t < my_tiles; ++t) {
             const int par = t & 1;
             const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-            int* ysp = ys + par * kTilePixels;
-            {   // class of pixel 32*sw + lane: first argmax of the EMA logits (prototype_handler.py:83-86)
-                const long long n = tile * kTilePixels + 32 * sw + lane;
-                int arg = -1;
-                if (n < p.N) {
-                    const long long bimg = n / HW, pix = n - bimg * HW;
-                    const float* lp = p.logits + (bimg * C) * (long long)HW + pix;
-                    float best = __ldg(lp);
-                    arg = 0;
-                    for (int k = 1; k < C; ++k) {
-                        const float v = __ldg(lp + (long long)k * HW);
-                        if (torch_greater(v, best)) { best = v; arg = k; }
-                    }
-                }
-                ysp[32 * sw + lane] = arg;
+            int* permp = perm + par * kTilePixels;
+            int* sclsp = scls + par * kTilePixels;
+            int* wc = wcnt + par * 4 * 36;
+            const long long t_ys0 = prof ? clock64() : 0;
+            // ---- stable counting sort of the tile's pixels by class (padding pixels form bucket 32, last)
+            const long long n = tile * kTilePixels + 32 * sw + lane;
+            const int y = (n < p.N) ? first_argmax<CP>(lv, C) : -1;
+            const int bucket = y < 0 ? 32 : y;
+            fetch_logits(t + 1);
+            const unsigned peers = __match_any_sync(0xffffffffu, bucket);
+            wc[sw * 36 + lane] = 0;
+            if (lane < 4) wc[sw * 36 + 32 + lane] = 0;
+            __syncwarp();
+            if ((peers & lt_mask) == 0) wc[sw * 36 + bucket] = __popc(peers);      // lowest lane of each class present
+            if (prof) { const long long t0 = clock64(); named_bar_sync(1, 128); dbg[1] += clock64() - t0; } else named_bar_sync(1, 128);
+            // lane l: size of class l over the tile, then an exclusive prefix over classes
+            const int tot = wc[lane] + wc[36 + lane] + wc[72 + lane] + wc[108 + lane];
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int n_valid = __shfl_sync(0xffffffffu, incl, 31);
+            int base = __shfl_sync(0xffffffffu, incl - tot, bucket & 31);
+            if (bucket == 32) base = n_valid;
+            for (int w2 = 0; w2 < sw; ++w2) base += wc[w2 * 36 + bucket];
+            const int pos = base + __popc(peers & lt_mask);
+            sclsp[pos] = y;
+            if (sw == 0 && lane < C) cnt[lane] += tot;                               // pixel counts per class
+            named_bar_sync(1, 128);
+            // sorted entry = pixel | last-of-its-class flag << 8 | class << 16 (class 0xFF = padding pixel)
+            {
+                const int nxt = pos + 1 < kTilePixels ? sclsp[pos + 1] : -2;
+                permp[pos] = (32 * sw + lane) | ((nxt != y) ? 0x100 : 0) | ((y & 0xFF) << 16);
             }
             named_bar_sync(1, 128);
-            if (sw == 0) {     // pixel counts per class
-                unsigned mask = 0;
-                int y[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    y[i] = ysp[32 * i + lane];
-                    mask |= (y[i] >= 0) ? (1u << y[i]) : 0u;
-                }
-                mask = __reduce_or_sync(0xffffffffu, mask);
-                while (mask) {
-                    const int k = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    int c = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) c += __popc(__ballot_sync(0xffffffffu, y[i] == k));
-                    if (lane == 0) cnt[k] += c;
-                }
-            }
+            if (prof) dbg[4] += clock64() - t_ys0;
+
             for (int b = sw; b < NB; b += 4) {
-                const long long q = (long long)t * NB + b;
-                const int stage = (int)(q % kTcStages);
-                const uint32_t use = (uint32_t)(q / kTcStages);
-                mbar_wait(full_t(stage), use & 1);
+                const long long q = (long long)t * NB + b;      // NB % 4 == 0, so q % 4 == b % 4 == sw
+                const int stage = sw;
+                const uint32_t use = (uint32_t)(q >> 2);
+                mbar_wait_t(full_t(stage), use & 1, prof, dbg[0]);
                 const int c = b * kTcChunkC + lane;
-                const float4* row = reinterpret_cast<const float4*>(Tst + ((size_t)stage * kTcChunkC + lane) * kTcRow);
-                const int4* ys4 = reinterpret_cast<const int4*>(ysp);
+                const float* row = Tst + ((size_t)stage * kTcChunkC + lane) * kTcRow;
+                const int4* ent4 = reinterpret_cast<const int4*>(permp);
                 float* a1 = acc + c;
                 float* a2 = acc + (size_t)C * D + c;
-                int cur = -1;
+                const long long t_seg0 = prof ? clock64() : 0;
+                // Walk the class-sorted entries with a running (sum, sum of squares); an entry flagged as the
+                // last of its class adds the running pair to that class's accumulators.  Every lane sees the
+                // same entries, so all branches are warp-uniform.
                 float s1 = 0.f, s2 = 0.f;
-                auto flush = [&]() {
-                    if (cur >= 0) {
-                        a1[(size_t)cur * D] += s1;
-                        a2[(size_t)cur * D] += s2;
-                    }
-                };
-                auto one = [&](int yv, float xv) {
-                    if (yv != cur) { flush(); cur = yv; s1 = 0.f; s2 = 0.f; }
-                    s1 += xv;
-                    s2 = fmaf(xv, xv, s2);
-                };
 #pragma unroll 4
-                for (int p4 = 0; p4 < kTilePixels / 4; ++p4) {
-                    const int4 yy = ys4[p4];
-                    const float4 v = row[p4];
-                    if (yy.x == cur && yy.y == cur && yy.z == cur && yy.w == cur) {
-                        s1 += (v.x + v.y) + (v.z + v.w);
-                        s2 += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+                for (int g = 0; g < kTilePixels / 4; ++g) {
+                    const int4 e4 = ent4[g];
+                    const float x0 = row[e4.x & 0xFF], x1 = row[e4.y & 0xFF], x2 = row[e4.z & 0xFF], x3 = row[e4.w & 0xFF];
+                    if (((e4.x | e4.y | e4.z | e4.w) & 0x100) == 0) {
+                        s1 += (x0 + x1) + (x2 + x3);
+                        s2 += fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
                     } else {
-                        one(yy.x, v.x); one(yy.y, v.y); one(yy.z, v.z); one(yy.w, v.w);
+                        const int ev[4] = {e4.x, e4.y, e4.z, e4.w};
+                        const float xv[4] = {x0, x1, x2, x3};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            s1 += xv[e];
+                            s2 = fmaf(xv[e], xv[e], s2);
+                            if (ev[e] & 0x100) {
+                                const int k = (ev[e] >> 16) & 0xFF;
+                                if (k != 0xFF) {
+                                    a1[k * D] += s1;
+                                    a2[k * D] += s2;
+                                }
+                                s1 = 0.f;
+                                s2 = 0.f;
+                            }
+                        }
                     }
                 }
-                flush();
+                if (prof) dbg[2] += clock64() - t_seg0;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_t(stage));
             }
@@ -417,6 +477,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     }
 
     // ---- teardown: publish the class partials, release tensor memory
+    if (prof && lane == 0) {
+        long long* d = p.debug + ((size_t)blockIdx.x * 32 + warp) * 8;
+        dbg[7] = clock64() - t_start;
+        for (int i = 0; i < 8; ++i) d[i] = dbg[i];
+    }
     tc_fence_before();
     __syncthreads();
     if (SUMS) {
@@ -433,14 +498,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
 // ---- host side -----------------------------------------------------------------------------------------
 bool tc_supported(int B, int D, int HW, int C) {
     (void)B; (void)HW;
-    return D % 32 == 0 && D >= 128 && D <= 256 && C >= 1 && C <= 32;
+    if (!(D % 128 == 0 && D >= 128 && D <= 256 && C >= 1 && C <= 32)) return false;   // D/32 must be a multiple of 4
+    return tc_smem(D, C, padded_classes(C), true).total <= 227 * 1024;   // per-CTA shared-memory limit on sm_100
 }
 
 int tc_grid(int tiles, int sms) { return tiles < sms ? tiles : sms; }
 
-template <int CP, bool SUMS>
+template <int CP, bool SUMS, bool WANT_DIST>
 static int launch_tc(const FusedParams& p, int grid, cudaStream_t stream) {
-    auto kern = fused_tc_kernel<CP, SUMS>;
+    auto kern = fused_tc_kernel<CP, SUMS, WANT_DIST>;
     const size_t smem = tc_smem(p.D, p.C, CP, SUMS).total;
     ONDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     timing_begin(stream);
@@ -451,10 +517,15 @@ static int launch_tc(const FusedParams& p, int grid, cudaStream_t stream) {
     return ONDA_OK;
 }
 
+template <int CP>
+static int launch_tc_cp(const FusedParams& p, int grid, bool sums, cudaStream_t stream) {
+    const bool dist = p.dist != nullptr;
+    if (sums) return dist ? launch_tc<CP, true, true>(p, grid, stream) : launch_tc<CP, true, false>(p, grid, stream);
+    return dist ? launch_tc<CP, false, true>(p, grid, stream) : launch_tc<CP, false, false>(p, grid, stream);
+}
+
 int launch_fused_tc(const FusedParams& p, int grid, bool sums, cudaStream_t stream) {
-    const int CP = padded_classes(p.C);
-    if (CP == 20) return sums ? launch_tc<20, true>(p, grid, stream) : launch_tc<20, false>(p, grid, stream);
-    return sums ? launch_tc<32, true>(p, grid, stream) : launch_tc<32, false>(p, grid, stream);
+    return padded_classes(p.C) == 20 ? launch_tc_cp<20>(p, grid, sums, stream) : launch_tc_cp<32>(p, grid, sums, stream);
 }
 
 }  // namespace onda

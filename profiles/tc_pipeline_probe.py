@@ -1,0 +1,33 @@
+"""Reads the tcgen05 kernel's per-warp wait counters (onda_debug_set_buffer) for the bench workload.
+Run on the GPU box:  python profiles/tc_pipeline_probe.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from onda_b200 import prototype_handler, _native as nat
+
+dev = torch.device("cuda:0")
+protos, sq, cnt, sets = bench.gpu_inputs(torch, dev, 256, 1, 1234)
+h = prototype_handler(impl="tcgen05", **bench.PARAMS)
+h.prototypes, h.squared_mean, h.counter = protos, sq, cnt
+lib = nat.load()
+feat, prior, out = sets[0]
+for _ in range(3):
+    h.pseudo_labels_fused(feat, prior, out); h.ma(feat, out)
+buf = torch.zeros(148 * 32 * 8, dtype=torch.int64, device=dev)
+lib.onda_debug_set_buffer(nat.ptr(buf))
+h.pseudo_labels_fused(feat, prior, out)
+torch.cuda.synchronize()
+lib.onda_debug_set_buffer(None)
+d = buf.view(148, 32, 8).double().cpu()
+tot = d[:, :, 7]
+names = {"loader": (0, 16, ["wait acc_empty", "wait empty_t(summer)", "wait empty_a(mma)", "wait global loads"]),
+         "epilogue": (16, 20, ["wait acc_full"]), "summer": (20, 24, ["wait full_t", "ys barrier", "summation loops", "-", "sort phase"]),
+         "mma": (24, 25, ["wait acc_empty", "wait full_a"])}
+print("mean total cycles per warp:", tot[:, :25].mean().item())
+for role, (a, b, labels) in names.items():
+    t = tot[:, a:b].mean().item()
+    print(f"{role:9s} total {t:10.0f} cyc")
+    for i, lab in enumerate(labels):
+        v = d[:, a:b, i].mean().item()
+        print(f"     {lab:24s} {v:10.0f} cyc  {100 * v / t:5.1f}%")

@@ -26,7 +26,8 @@ IMPLS = ["simt", "tcgen05"]
 
 def need_shape(impl, D, C=19):
     """The tcgen05 kernel covers D % 32 == 0, 128 <= D <= 256, C <= 32; everything else is the CUDA-core kernel."""
-    if impl == "tcgen05" and not (D % 32 == 0 and 128 <= D <= 256 and C <= 32):
+    from onda_b200 import _native as nat
+    if impl == "tcgen05" and not nat.load().onda_impl_supported(1, D, 128, C, nat.IMPL["tcgen05"]):
         pytest.skip(f"tcgen05 kernel does not cover D={D}, C={C}")
 
 
@@ -137,7 +138,11 @@ def test_fused_equals_separate_calls(impl):
     soft_s = hs[1].pseudo_labels(feat, prior, soft=True)
     hs[1].ma(feat, out)
     assert torch.equal(labels_f, labels_s) and torch.equal(soft_f, soft_s)
-    assert torch.equal(hs[0].prototypes, hs[1].prototypes) and torch.equal(hs[0].squared_mean, hs[1].squared_mean)
+    if impl == "simt":
+        assert torch.equal(hs[0].prototypes, hs[1].prototypes) and torch.equal(hs[0].squared_mean, hs[1].squared_mean)
+    else:   # the separate ma() call has no distance output and runs the CUDA-core class-sum kernel: same sums, other order
+        close_rel_max(hs[0].prototypes, hs[1].prototypes.cpu(), 1e-6)
+        close_rel_max(hs[0].squared_mean, hs[1].squared_mean.cpu(), 1e-6)
 
 
 def test_hard_then_soft_reuses_launch_only_for_same_tensors():
@@ -187,7 +192,7 @@ SHAPES = [
     (39, 2, 320, 3, 51, 19, "mahalanobis"),       # HW = 153
     (40, 2, 128, 21, 13, 19, "mahalanobis"),      # tcgen05 range: D = 128, ragged last tile
     (42, 3, 192, 5, 31, 7, "euclidean"),          # D = 192 (6 chunks), few classes
-    (43, 1, 256, 9, 14, 25, "mahalanobis"),       # 25 classes (32-wide epilogue), 126 pixels: a single partial tile
+    (43, 1, 128, 9, 14, 25, "mahalanobis"),       # 25 classes (32-wide epilogue), 126 pixels: a single partial tile
     (44, 7, 160, 37, 53, 19, "mahalanobis"),      # D = 160 (5 chunks), 13727 pixels
 ]
 
