@@ -18,13 +18,16 @@
 //                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory.
 //   warps 16-19  epilogue: tcgen05.ld of the 32 accumulator columns of their pixel, then the common
 //                per-pixel tail (epilogue.cuh): sqrt, softmax, prior rectification, label, statistics.
-//   warps 20-23  class sums: lane = channel walks the 128 pixels of a staged chunk with run-length
-//                accumulation into shared-memory accumulators that the warp alone owns (fixed
-//                summation order, no atomics); also computes the per-pixel class (argmax of logits).
-// Stages: one {64 TMEM columns (hi|lo), 32x132-float smem tile} pair per loader group, so every
-// mbarrier has exactly one producer side and one consumer side that visit it in order (a parity
-// wait is never more than one phase away from the barrier); class-sum warp s consumes the tiles of
-// loader group s, which with D/32 a multiple of 4 is always the same set of channel blocks.
+//   warps 20-23  class sums: per tile the 128 pixels are counting-sorted by class (argmax of the EMA
+//                logits) and the sorted order is cut at class boundaries into four ranges, one per warp.
+//                For every staged 64-channel block, lane = channel PAIR walks the warp's classes with
+//                packed f32x2 adds (FADD2/FFMA2 on 8-byte shared-memory loads) and updates each class's
+//                shared-memory accumulators once.  A class belongs to exactly one warp per tile and the
+//                warps re-synchronise between tiles: fixed summation order, no atomics.
+// Stages: 64 TMEM columns (hi|lo) per loader group; two shared-memory tiles [128 pixels][64 channels]
+// for the class sums, tile P%2 filled by loader groups {0,1} (P even) or {2,3} (P odd), P = index of
+// the 64-channel block pair in the chunk sequence.  Every mbarrier is visited phase by phase, in
+// order, by each of its waiters (a parity wait is never more than one phase away from the barrier).
 // Two accumulator buffers of 32 TMEM columns.  tcgen05.commit frees A stages / publishes accumulators.
 #include "epilogue.cuh"
 
@@ -36,7 +39,8 @@ constexpr int kTcSumWarp0 = 20;
 constexpr int kTcMmaWarp = 24;
 constexpr int kTcThreads = 25 * 32;
 constexpr int kTcStages = 4;                     // = loader groups
-constexpr int kTcRow = kTilePixels + 5;          // padded (odd) row of a staged chunk: lane = channel reads any pixel column conflict-free
+constexpr int kTcTRow = 66;                      // floats per pixel row of a class-sum tile: 64 channels + 2 (conflict-free STS.64 / LDS.64)
+constexpr int kTcTStages = 2;
 constexpr int kTcChunkC = 32;                    // channels per chunk
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = kTcStages * 64;    // accumulators after the A stages
@@ -51,12 +55,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// One non-blocking probe of an mbarrier phase.
+// One non-blocking probe of an mbarrier phase (test_wait: try_wait may park in the shared-memory pipeline
+// for a hardware time-out, and ~20 parked waiters starve the LDS/STS of the working warps).
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
@@ -93,6 +98,28 @@ __device__ __forceinline__ uint32_t cvt_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// packed fp32 pairs (sm_100 FADD2 / FFMA2): one instruction, two channels
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -138,14 +165,14 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------
 struct TcSmem {
-    size_t bhi, blo, tiles, acc, out, apart, mu, w, perm, scls, wc, cnt, red, bars, tmem_ptr, total;  // byte offsets
+    size_t bhi, blo, tiles, acc, out, apart, mu, w, perm, scls, wc, offs, cnt, red, bars, tmem_ptr, total;  // byte offsets
 };
 __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     TcSmem s;
     size_t o = 0;
     s.bhi = o; o += (size_t)32 * D * 4;
     s.blo = o; o += (size_t)32 * D * 4;
-    s.tiles = o; o += sums ? (size_t)kTcStages * kTcChunkC * kTcRow * 4 : 0;
+    s.tiles = o; o += sums ? (size_t)kTcTStages * kTilePixels * kTcTRow * 4 : 0;
     s.acc = o; o += sums ? (size_t)2 * C * D * 4 : 0;
     s.out = o; o += (size_t)kTilePixels * (CP + 1) * 4;
     s.apart = o; o += (size_t)2 * (D / kTcChunkC) * kTilePixels * 4;
@@ -154,6 +181,7 @@ __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     s.perm = o; o += (size_t)2 * kTilePixels * 4;      // class-sorted order -> pixel of the tile (per tile parity)
     s.scls = o; o += (size_t)2 * kTilePixels * 4;      // class of each sorted entry (-1 = padding pixel)
     s.wc = o; o += (size_t)2 * 4 * 36 * 4;             // per-warp class histograms
+    s.offs = o; o += (size_t)2 * 36 * 4;               // start of every class in the sorted order
     s.cnt = o; o += 32 * 4;
     s.red = o; o += 4 * kStatSlots * 4;
     s.bars = o; o += (size_t)(4 * kTcStages + 4) * 8;
@@ -180,6 +208,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     int* perm = reinterpret_cast<int*>(smem_raw + L.perm);
     int* scls = reinterpret_cast<int*>(smem_raw + L.scls);
     int* wcnt = reinterpret_cast<int*>(smem_raw + L.wc);
+    int* coffs = reinterpret_cast<int*>(smem_raw + L.offs);
     int* cnt = reinterpret_cast<int*>(smem_raw + L.cnt);
     float* red = reinterpret_cast<float*>(smem_raw + L.red);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.tmem_ptr);
@@ -209,8 +238,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         for (int s = 0; s < kTcStages; ++s) {
             mbar_init(full_a(s), 128);
             mbar_init(empty_a(s), 1);
-            mbar_init(full_t(s), 128);
-            mbar_init(empty_t(s), 1);
+            mbar_init(full_t(s), 256);
+            mbar_init(empty_t(s), 4);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(acc_full(i), 1);
@@ -232,24 +261,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_start = clock64();
     const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const long long total_chunks = (long long)my_tiles * NB;
+    const int total_chunks = my_tiles * NB;
 
     if (warp < kTcLoaderWarps) {
         // =========================== loaders ===========================================
         const int quarter = warp & 3, group = warp >> 2;
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
-        for (long long q = group; q < total_chunks; q += 4) {
-            const int t = (int)(q / NB), b = (int)(q - (long long)t * NB);
+        const unsigned HWu = (unsigned)HW, Nu = (unsigned)p.N;
+        for (int q = group; q < total_chunks; q += 4) {
+            const int t = q / NB, b = q - t * NB;
             const int par = t & 1, stage = group;
-            const uint32_t use = (uint32_t)(q >> 2);
-            const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-            long long n = tile * kTilePixels + 32 * quarter + lane;
-            if (n >= p.N) n = p.N - 1;       // clamp: results of padded rows are never stored (epilogue / ys guard them)
-            const long long bimg = n / HW, pix = n - bimg * HW;
-            const float* src = p.feat + (bimg * D + (long long)b * kTcChunkC) * HW + pix;
+            const uint32_t use = (uint32_t)q >> 2;
+            const int pair = q >> 1, tstage = pair & 1;              // 64-channel block pair of the chunk sequence
+            const uint32_t tuse = (uint32_t)pair >> 1;
+            const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
+            unsigned n = tile * kTilePixels + 32 * quarter + lane;
+            n = n < Nu ? n : Nu - 1;         // clamp: results of padded rows are never stored (epilogue / class sort guard them)
+            const unsigned bimg = n / HWu, pix = n - bimg * HWu;
+            const char* src = reinterpret_cast<const char*>(p.feat + ((size_t)bimg * D + (size_t)b * kTcChunkC) * HWu + pix);
+            const size_t plane = (size_t)HWu * sizeof(float);       // one 64-bit add per load, no multiplies
             float x[kTcChunkC];
 #pragma unroll
-            for (int j = 0; j < kTcChunkC; ++j) x[j] = ldg_stream(src + (long long)j * HW);
+            for (int j = 0; j < kTcChunkC; ++j) {
+                x[j] = ldg_stream(reinterpret_cast<const float*>(src));
+                src += plane;
+            }
             if (prof) {   // time until the last of the 32 loads has landed
                 const long long t0 = clock64();
                 uint32_t sink;
@@ -258,27 +294,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             }
 
             if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // apart[par] of tile t-2 consumed
-            if (SUMS) {
-                mbar_wait_t(empty_t(stage), (use & 1) ^ 1, prof, dbg[1]);
-                float* trow = Tst + (size_t)stage * kTcChunkC * kTcRow + 32 * quarter + lane;
+            if (SUMS) {   // raw values, pixel-major, two channels per 8-byte store
+                mbar_wait_t(empty_t(tstage), (tuse & 1) ^ 1, prof, dbg[1]);
+                float2* trow = reinterpret_cast<float2*>(Tst + ((size_t)tstage * kTilePixels + 32 * quarter + lane) * kTcTRow +
+                                                         (b & 1) * kTcChunkC);
 #pragma unroll
-                for (int j = 0; j < kTcChunkC; ++j) trow[j * kTcRow] = x[j];
-                mbar_arrive(full_t(stage));
+                for (int j = 0; j < kTcChunkC / 2; ++j) trow[j] = make_float2(x[2 * j], x[2 * j + 1]);
+                mbar_arrive(full_t(tstage));
             }
             mbar_wait_t(empty_a(stage), (use & 1) ^ 1, prof, dbg[2]);
             tc_fence_after();
             float a = 0.f;
             const uint32_t tcol = tmem_base + lane_base + (uint32_t)stage * 64;
+            const float4* mu4 = reinterpret_cast<const float4*>(mus + b * kTcChunkC);
+            const float4* w4 = reinterpret_cast<const float4*>(wsm + b * kTcChunkC);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = b * kTcChunkC + half * 16 + j;
-                    const float xc = x[half * 16 + j] - mus[c];
-                    a = fmaf(xc * xc, wsm[c], a);
-                    hi[j] = cvt_tf32(xc);
-                    lo[j] = __float_as_uint(xc - __uint_as_float(hi[j]));
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 m = mu4[half * 4 + j4], wv = w4[half * 4 + j4];
+                    const float mm[4] = {m.x, m.y, m.z, m.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = j4 * 4 + e;
+                        const float xc = x[half * 16 + j] - mm[e];
+                        a = fmaf(xc * xc, ww[e], a);
+                        hi[j] = (__float_as_uint(xc) + 0x1000u) & 0xffffe000u;      // round to TF32 (10-bit mantissa)
+                        lo[j] = __float_as_uint(xc - __uint_as_float(hi[j]));       // exact remainder
+                    }
                 }
                 tc_st16(tcol + half * 16, hi);
                 tc_st16(tcol + 32 + half * 16, lo);
@@ -392,6 +436,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             int* permp = perm + par * kTilePixels;
             int* sclsp = scls + par * kTilePixels;
             int* wc = wcnt + par * 4 * 36;
+            int* offp = coffs + par * 36;
             const long long t_ys0 = prof ? clock64() : 0;
             // ---- stable counting sort of the tile's pixels by class (padding pixels form bucket 32, last)
             const long long n = tile * kTilePixels + 32 * sw + lane;
@@ -413,6 +458,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 if (lane >= o) incl += v;
             }
             const int n_valid = __shfl_sync(0xffffffffu, incl, 31);
+            const unsigned present = __ballot_sync(0xffffffffu, tot > 0 && lane < C);   // classes with pixels in this tile
+            if (sw == 0) {
+                offp[lane] = incl - tot;
+                if (lane == 31) offp[32] = incl;
+            }
+            // this warp's share of the sorted order: the classes whose run starts in [lo, hi), with the cuts at the
+            // first class boundary at or after entries 32, 64 and 96
+            const int cstart = incl - tot;
+            const bool has = tot > 0 && lane < C;
+            const int lo_cut = sw == 0 ? 0 : (int)__reduce_min_sync(0xffffffffu, (unsigned)((has && cstart >= 32 * sw) ? cstart : n_valid));
+            const int hi_cut = sw == 3 ? kTilePixels + 1 : (int)__reduce_min_sync(0xffffffffu, (unsigned)((has && cstart >= 32 * (sw + 1)) ? cstart : n_valid + 1));
+            const unsigned mine = __ballot_sync(0xffffffffu, has && cstart >= lo_cut && cstart < hi_cut);
             int base = __shfl_sync(0xffffffffu, incl - tot, bucket & 31);
             if (bucket == 32) base = n_valid;
             for (int w2 = 0; w2 < sw; ++w2) base += wc[w2 * 36 + bucket];
@@ -420,58 +477,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             sclsp[pos] = y;
             if (sw == 0 && lane < C) cnt[lane] += tot;                               // pixel counts per class
             named_bar_sync(1, 128);
-            // sorted entry = pixel | last-of-its-class flag << 8 | class << 16 (class 0xFF = padding pixel)
+            // sorted entry -> row offset of its pixel; sclsp holds the class of each sorted entry (-1 = padding)
             {
-                const int nxt = pos + 1 < kTilePixels ? sclsp[pos + 1] : -2;
-                permp[pos] = (32 * sw + lane) | ((nxt != y) ? 0x100 : 0) | ((y & 0xFF) << 16);
+                permp[pos] = (32 * sw + lane) * (kTcTRow * 4);      // byte offset of the pixel's row in a class-sum tile
             }
             named_bar_sync(1, 128);
             if (prof) dbg[4] += clock64() - t_ys0;
 
-            for (int b = sw; b < NB; b += 4) {
-                const long long q = (long long)t * NB + b;      // NB % 4 == 0, so q % 4 == b % 4 == sw
-                const int stage = sw;
-                const uint32_t use = (uint32_t)(q >> 2);
-                mbar_wait_t(full_t(stage), use & 1, prof, dbg[0]);
-                const int c = b * kTcChunkC + lane;
-                const float* row = Tst + ((size_t)stage * kTcChunkC + lane) * kTcRow;
-                const int4* ent4 = reinterpret_cast<const int4*>(permp);
-                float* a1 = acc + c;
-                float* a2 = acc + (size_t)C * D + c;
+            const int pairs = NB / 2;
+            for (int j = 0; j < pairs; ++j) {
+                const int pair = t * pairs + j, tstage = pair & 1;
+                mbar_wait_t(full_t(tstage), ((uint32_t)pair >> 1) & 1, prof, dbg[0]);
                 const long long t_seg0 = prof ? clock64() : 0;
-                // Walk the class-sorted entries with a running (sum, sum of squares); an entry flagged as the
-                // last of its class adds the running pair to that class's accumulators.  Every lane sees the
-                // same entries, so all branches are warp-uniform.
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-                for (int g = 0; g < kTilePixels / 4; ++g) {
-                    const int4 e4 = ent4[g];
-                    const float x0 = row[e4.x & 0xFF], x1 = row[e4.y & 0xFF], x2 = row[e4.z & 0xFF], x3 = row[e4.w & 0xFF];
-                    if (((e4.x | e4.y | e4.z | e4.w) & 0x100) == 0) {
-                        s1 += (x0 + x1) + (x2 + x3);
-                        s2 += fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
-                    } else {
-                        const int ev[4] = {e4.x, e4.y, e4.z, e4.w};
-                        const float xv[4] = {x0, x1, x2, x3};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            s1 += xv[e];
-                            s2 = fmaf(xv[e], xv[e], s2);
-                            if (ev[e] & 0x100) {
-                                const int k = (ev[e] >> 16) & 0xFF;
-                                if (k != 0xFF) {
-                                    a1[k * D] += s1;
-                                    a2[k * D] += s2;
-                                }
-                                s1 = 0.f;
-                                s2 = 0.f;
-                            }
-                        }
+                // lane = channels (64j + 2*lane, +1).  One pass per class of this warp's range (warp-uniform mask):
+                // packed (sum, sum of squares) over the class's run of sorted entries, then one accumulator update.
+                const uint32_t rowbase = smem_u32(Tst + (size_t)tstage * kTilePixels * kTcTRow) + 8u * lane;
+                const uint32_t a1 = smem_u32(acc) + 4u * (64 * j + 2 * lane);
+                const uint32_t a2 = a1 + 4u * C * D;
+                unsigned todo = mine;
+                while (todo) {
+                    const int k = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    int i = offp[k];
+                    const int i1 = offp[k + 1];
+                    uint64_t s1 = 0, s2 = 0;
+                    for (; i + 4 <= i1; i += 4) {
+                        const uint64_t x0 = lds64(rowbase + permp[i]), x1 = lds64(rowbase + permp[i + 1]);
+                        const uint64_t x2 = lds64(rowbase + permp[i + 2]), x3 = lds64(rowbase + permp[i + 3]);
+                        s1 = fadd2(s1, fadd2(fadd2(x0, x1), fadd2(x2, x3)));
+                        s2 = fadd2(s2, fadd2(ffma2(x0, x0, fmul2(x1, x1)), ffma2(x2, x2, fmul2(x3, x3))));
                     }
+                    for (; i < i1; ++i) {
+                        const uint64_t x0 = lds64(rowbase + permp[i]);
+                        s1 = fadd2(s1, x0);
+                        s2 = ffma2(x0, x0, s2);
+                    }
+                    const uint32_t off = 4u * k * D;
+                    sts64(a1 + off, fadd2(lds64(a1 + off), s1));
+                    sts64(a2 + off, fadd2(lds64(a2 + off), s2));
                 }
                 if (prof) dbg[2] += clock64() - t_seg0;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty_t(stage));
+                if (lane == 0) mbar_arrive(empty_t(tstage));
             }
         }
     }
@@ -498,7 +545,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
 // ---- host side -----------------------------------------------------------------------------------------
 bool tc_supported(int B, int D, int HW, int C) {
     (void)B; (void)HW;
-    if (!(D % 128 == 0 && D >= 128 && D <= 256 && C >= 1 && C <= 32)) return false;   // D/32 must be a multiple of 4
+    if (!(D % 128 == 0 && D >= 128 && D <= 256 && C >= 1 && C <= 32)) return false;   // D/64 block pairs: 2 or 4
     return tc_smem(D, C, padded_classes(C), true).total <= 227 * 1024;   // per-CTA shared-memory limit on sm_100
 }
 
