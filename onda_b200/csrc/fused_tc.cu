@@ -6,44 +6,40 @@
 //     x' . Q  =  hi(x').hi(Q) + hi(x').lo(Q) + lo(x').hi(Q)      (fp32 accumulate in TMEM)
 // which keeps fp32-level accuracy (the dropped lo.lo term is 2^-22 relative).
 //
-// One persistent CTA per SM, 25 warps, warp-specialised over a single global chunk sequence
-// (chunk = 128 pixels x 32 channels; a tile of 128 pixels is D/32 consecutive chunks):
-//   warps  0-15  loaders: lane = pixel.  Coalesced 4-byte loads along the NCHW channel planes, then
-//                (a) raw values -> shared-memory transposition tile [channel][pixel] for the class sums,
-//                (b) centred values split into TF32 hi/lo -> TMEM (tcgen05.st) as the A operand
-//                    (lane = pixel, column = channel), (c) sum_j w_j x'_j^2 on the CUDA cores.
-//                Warp w may only touch TMEM lanes 32*(w%4)..+31, so w%4 is the pixel quarter and
-//                w/4 the loader group; group g takes chunks g, g+4, g+8, ...
-//   warp   24    MMA issuer: per chunk 4 K-steps x 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
-//                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory.
+// One persistent CTA per SM, 25 warps, over a single global chunk sequence (chunk = 128 pixels x
+// 32 channels; a tile of 128 pixels is D/32 consecutive chunks):
+//   warps  0-15  workers, four groups of four; warp w%4 is the pixel quarter (the only TMEM lanes a warp
+//                may touch are 32*(w%4)..+31), w/4 the group; group g takes chunks g, g+4, g+8, ...
+//                Per chunk: (1) lane = pixel: coalesced 4-byte loads along the NCHW channel planes;
+//                (2) raw values -> the group's shared-memory tile [pixel][channel]; (3) centred values,
+//                split into TF32 hi/lo -> TMEM (tcgen05.st) as the A operand (lane = pixel, column =
+//                channel) and sum_j w_j x'_j^2 on the CUDA cores; (4) class sums of the chunk: lane =
+//                channel, each of the group's four warps walks its quarter of the class-sorted pixels
+//                (cut at class boundaries) and updates every class's shared-memory accumulators once.
+//                A class/channel pair has exactly one owner per tile and the group re-synchronises per
+//                chunk: fixed summation order, no atomics.
 //   warps 16-19  epilogue: tcgen05.ld of the 32 accumulator columns of their pixel, then the common
 //                per-pixel tail (epilogue.cuh): sqrt, softmax, prior rectification, label, statistics.
-//   warps 20-23  class sums: per tile the 128 pixels are counting-sorted by class (argmax of the EMA
-//                logits) and the sorted order is cut at class boundaries into four ranges, one per warp.
-//                For every staged 64-channel block, lane = channel PAIR walks the warp's classes with
-//                packed f32x2 adds (FADD2/FFMA2 on 8-byte shared-memory loads) and updates each class's
-//                shared-memory accumulators once.  A class belongs to exactly one warp per tile and the
-//                warps re-synchronise between tiles: fixed summation order, no atomics.
-// Stages: 64 TMEM columns (hi|lo) per loader group; two shared-memory tiles [128 pixels][64 channels]
-// for the class sums, tile P%2 filled by loader groups {0,1} (P even) or {2,3} (P odd), P = index of
-// the 64-channel block pair in the chunk sequence.  Every mbarrier is visited phase by phase, in
-// order, by each of its waiters (a parity wait is never more than one phase away from the barrier).
-// Two accumulator buffers of 32 TMEM columns.  tcgen05.commit frees A stages / publishes accumulators.
+//   warps 20-23  sorter: per tile, class of every pixel (first argmax of the EMA logits) and a stable
+//                counting sort of the 128 pixels by class, published for the workers (double-buffered).
+//   warp   24    MMA issuer: per chunk 4 K-steps x 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
+//                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory.
+// Every mbarrier has one producer side and one consumer side that visit it phase by phase, in order.
+// Two accumulator buffers of 32 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
 #include "epilogue.cuh"
 
 namespace onda {
 
-constexpr int kTcLoaderWarps = 16;
+constexpr int kTcWorkerWarps = 16;
 constexpr int kTcEpiWarp0 = 16;
-constexpr int kTcSumWarp0 = 20;
+constexpr int kTcSortWarp0 = 20;
 constexpr int kTcMmaWarp = 24;
 constexpr int kTcThreads = 25 * 32;
-constexpr int kTcStages = 4;                     // = loader groups
-constexpr int kTcTRow = 66;                      // floats per pixel row of a class-sum tile: 64 channels + 2 (conflict-free STS.64 / LDS.64)
-constexpr int kTcTStages = 2;
+constexpr int kTcGroups = 4;                     // worker groups = TMEM A stages = class-sum tiles
 constexpr int kTcChunkC = 32;                    // channels per chunk
+constexpr int kTcTRow = 34;                      // floats per pixel row of a class-sum tile: 32 channels + 2 (conflict-free STS.64 and LDS.32)
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kAccCol0 = kTcStages * 64;    // accumulators after the A stages
+constexpr uint32_t kAccCol0 = kTcGroups * 64;    // accumulators after the A stages
 constexpr uint32_t kSpinLimit = 20000000u;       // failed probes (each followed by a <=256 ns sleep) before giving up
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -165,26 +161,26 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------
 struct TcSmem {
-    size_t bhi, blo, tiles, acc, out, apart, mu, w, perm, scls, wc, offs, cnt, red, bars, tmem_ptr, total;  // byte offsets
+    size_t bhi, blo, tiles, acc, out, apart, mu, w, eoff, ecls, cuts, wc, cnt, red, bars, tmem_ptr, total;  // byte offsets
 };
 __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     TcSmem s;
     size_t o = 0;
     s.bhi = o; o += (size_t)32 * D * 4;
     s.blo = o; o += (size_t)32 * D * 4;
-    s.tiles = o; o += sums ? (size_t)kTcTStages * kTilePixels * kTcTRow * 4 : 0;
+    s.tiles = o; o += sums ? (size_t)kTcGroups * kTilePixels * kTcTRow * 4 : 0;
     s.acc = o; o += sums ? (size_t)2 * C * D * 4 : 0;
     s.out = o; o += (size_t)kTilePixels * (CP + 1) * 4;
     s.apart = o; o += (size_t)2 * (D / kTcChunkC) * kTilePixels * 4;
     s.mu = o; o += (size_t)D * 4;
     s.w = o; o += (size_t)D * 4;
-    s.perm = o; o += (size_t)2 * kTilePixels * 4;      // class-sorted order -> pixel of the tile (per tile parity)
-    s.scls = o; o += (size_t)2 * kTilePixels * 4;      // class of each sorted entry (-1 = padding pixel)
-    s.wc = o; o += (size_t)2 * 4 * 36 * 4;             // per-warp class histograms
-    s.offs = o; o += (size_t)2 * 36 * 4;               // start of every class in the sorted order
+    s.eoff = o; o += (size_t)2 * kTilePixels * 4;      // per tile parity: row offset of every class-sorted entry
+    s.ecls = o; o += (size_t)2 * kTilePixels * 4;      // ... and its class (-1 = padding pixel)
+    s.cuts = o; o += (size_t)2 * 8 * 4;                // ... and the four class-aligned ranges of the sorted order
+    s.wc = o; o += (size_t)4 * 36 * 4;                 // per-warp class histograms of the sorter
     s.cnt = o; o += 32 * 4;
     s.red = o; o += 4 * kStatSlots * 4;
-    s.bars = o; o += (size_t)(4 * kTcStages + 4) * 8;
+    s.bars = o; o += (size_t)(2 * kTcGroups + 8) * 8;
     s.tmem_ptr = o; o += 16;
     s.total = o;
     return s;
@@ -205,20 +201,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     float* apart = reinterpret_cast<float*>(smem_raw + L.apart);
     float* mus = reinterpret_cast<float*>(smem_raw + L.mu);
     float* wsm = reinterpret_cast<float*>(smem_raw + L.w);
-    int* perm = reinterpret_cast<int*>(smem_raw + L.perm);
-    int* scls = reinterpret_cast<int*>(smem_raw + L.scls);
-    int* wcnt = reinterpret_cast<int*>(smem_raw + L.wc);
-    int* coffs = reinterpret_cast<int*>(smem_raw + L.offs);
+    int* eoff = reinterpret_cast<int*>(smem_raw + L.eoff);
+    int* ecls = reinterpret_cast<int*>(smem_raw + L.ecls);
+    int* cuts = reinterpret_cast<int*>(smem_raw + L.cuts);
+    int* wc = reinterpret_cast<int*>(smem_raw + L.wc);
     int* cnt = reinterpret_cast<int*>(smem_raw + L.cnt);
     float* red = reinterpret_cast<float*>(smem_raw + L.red);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.tmem_ptr);
     const uint32_t bars = smem_u32(smem_raw + L.bars);
     auto full_a = [&](int s) { return bars + 8u * s; };
-    auto empty_a = [&](int s) { return bars + 8u * (kTcStages + s); };
-    auto full_t = [&](int s) { return bars + 8u * (2 * kTcStages + s); };
-    auto empty_t = [&](int s) { return bars + 8u * (3 * kTcStages + s); };
-    auto acc_full = [&](int i) { return bars + 8u * (4 * kTcStages + i); };
-    auto acc_empty = [&](int i) { return bars + 8u * (4 * kTcStages + 2 + i); };
+    auto empty_a = [&](int s) { return bars + 8u * (kTcGroups + s); };
+    auto acc_full = [&](int i) { return bars + 8u * (2 * kTcGroups + i); };
+    auto acc_empty = [&](int i) { return bars + 8u * (2 * kTcGroups + 2 + i); };
+    auto sort_ready = [&](int i) { return bars + 8u * (2 * kTcGroups + 4 + i); };
+    auto sort_free = [&](int i) { return bars + 8u * (2 * kTcGroups + 6 + i); };
 
     const TableLayout T = table_layout(C, D);
     // ---- one-time setup: tables to shared memory, barriers, tensor memory
@@ -235,15 +231,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         if (tid < 32) cnt[tid] = 0;
     }
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) {
+        for (int s = 0; s < kTcGroups; ++s) {
             mbar_init(full_a(s), 128);
             mbar_init(empty_a(s), 1);
-            mbar_init(full_t(s), 256);
-            mbar_init(empty_t(s), 4);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(acc_full(i), 1);
             mbar_init(acc_empty(i), 128);
+            mbar_init(sort_ready(i), 128);
+            mbar_init(sort_free(i), kTcWorkerWarps);
         }
         fence_barrier_init();
     }
@@ -262,50 +258,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     const long long t_start = clock64();
     const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_chunks = my_tiles * NB;
+    const unsigned HWu = (unsigned)HW, Nu = (unsigned)p.N;
 
-    if (warp < kTcLoaderWarps) {
-        // =========================== loaders ===========================================
+    if (warp < kTcWorkerWarps) {
+        // =========================== workers ===========================================
         const int quarter = warp & 3, group = warp >> 2;
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
-        const unsigned HWu = (unsigned)HW, Nu = (unsigned)p.N;
-        for (int q = group; q < total_chunks; q += 4) {
+        float* Tg = Tst + (size_t)group * kTilePixels * kTcTRow;
+        const uint32_t tg_lane = smem_u32(Tg) + 4u * lane;           // class sums: lane = channel of the chunk
+        const int gbar = 3 + group;                                   // named barrier of the group (128 threads)
+        float x[kTcChunkC];
+        auto issue_loads = [&](int q) {
             const int t = q / NB, b = q - t * NB;
-            const int par = t & 1, stage = group;
-            const uint32_t use = (uint32_t)q >> 2;
-            const int pair = q >> 1, tstage = pair & 1;              // 64-channel block pair of the chunk sequence
-            const uint32_t tuse = (uint32_t)pair >> 1;
             const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
             unsigned n = tile * kTilePixels + 32 * quarter + lane;
-            n = n < Nu ? n : Nu - 1;         // clamp: results of padded rows are never stored (epilogue / class sort guard them)
+            n = n < Nu ? n : Nu - 1;         // clamp: results of padded rows are never stored (epilogue / sorter guard them)
             const unsigned bimg = n / HWu, pix = n - bimg * HWu;
             const char* src = reinterpret_cast<const char*>(p.feat + ((size_t)bimg * D + (size_t)b * kTcChunkC) * HWu + pix);
             const size_t plane = (size_t)HWu * sizeof(float);       // one 64-bit add per load, no multiplies
-            float x[kTcChunkC];
 #pragma unroll
             for (int j = 0; j < kTcChunkC; ++j) {
                 x[j] = ldg_stream(reinterpret_cast<const float*>(src));
                 src += plane;
             }
-            if (prof) {   // time until the last of the 32 loads has landed
-                const long long t0 = clock64();
-                uint32_t sink;
-                asm volatile("mov.b32 %0, %1;" : "=r"(sink) : "f"(x[kTcChunkC - 1]));
-                dbg[3] += clock64() - t0 + (sink == 0x7fc12345u ? 1 : 0);
-            }
-
-            if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // apart[par] of tile t-2 consumed
-            if (SUMS) {   // raw values, pixel-major, two channels per 8-byte store
-                mbar_wait_t(empty_t(tstage), (tuse & 1) ^ 1, prof, dbg[1]);
-                float2* trow = reinterpret_cast<float2*>(Tst + ((size_t)tstage * kTilePixels + 32 * quarter + lane) * kTcTRow +
-                                                         (b & 1) * kTcChunkC);
+        };
+        if (group < total_chunks) issue_loads(group);
+        for (int q = group; q < total_chunks; q += kTcGroups) {
+            const int t = q / NB, b = q - t * NB;
+            const int par = t & 1;
+            const uint32_t use = (uint32_t)q >> 2;
+            if (SUMS) {   // raw values into the group's tile, pixel-major, two channels per 8-byte store
+                float2* trow = reinterpret_cast<float2*>(Tg + (size_t)(32 * quarter + lane) * kTcTRow);
 #pragma unroll
                 for (int j = 0; j < kTcChunkC / 2; ++j) trow[j] = make_float2(x[2 * j], x[2 * j + 1]);
-                mbar_arrive(full_t(tstage));
+                named_bar_sync(gbar, 128);          // all 128 pixels of the chunk are staged
             }
-            mbar_wait_t(empty_a(stage), (use & 1) ^ 1, prof, dbg[2]);
+            if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // apart[par] of tile t-2 consumed
+            mbar_wait_t(empty_a(group), (use & 1) ^ 1, prof, dbg[2]);
             tc_fence_after();
             float a = 0.f;
-            const uint32_t tcol = tmem_base + lane_base + (uint32_t)stage * 64;
+            const uint32_t tcol = tmem_base + lane_base + (uint32_t)group * 64;
             const float4* mu4 = reinterpret_cast<const float4*>(mus + b * kTcChunkC);
             const float4* w4 = reinterpret_cast<const float4*>(wsm + b * kTcChunkC);
 #pragma unroll
@@ -330,7 +322,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             apart[((size_t)par * NB + b) * kTilePixels + 32 * quarter + lane] = a;
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(full_a(stage));
+            mbar_arrive(full_a(group));
+            if (q + kTcGroups < total_chunks) issue_loads(q + kTcGroups);     // next chunk's loads fly during the class sums
+
+            if (SUMS) {
+                // ---- class sums of this chunk's 32 channels (lane = channel) over this warp's quarter of the
+                // class-sorted pixels.  Lane e keeps entry e's row offset and class in registers (broadcast by
+                // shuffle: no dependent shared-memory loads), eight loads are in flight at once, and the class
+                // ends are a warp-uniform bit mask: an end adds the running (sum, sum of squares) to that class.
+                mbar_wait_t(sort_ready(par), ((uint32_t)t >> 1) & 1, prof, dbg[1]);
+                const long long t_seg0 = prof ? clock64() : 0;
+                const int* eo = eoff + par * kTilePixels;
+                const int* ec = ecls + par * kTilePixels;
+                const int lo_cut = cuts[par * 8 + quarter], hi_cut = cuts[par * 8 + quarter + 1];
+                float* a1 = acc + b * kTcChunkC + lane;
+                float* a2 = a1 + (size_t)C * D;
+                float s1 = 0.f, s2 = 0.f;
+                for (int blk = lo_cut; blk < hi_cut; blk += 32) {
+                    const int idx = blk + lane;
+                    const bool live = idx < hi_cut;
+                    const int myoff = live ? eo[idx] : 0;
+                    const int mycls = live ? ec[idx] : -1;
+                    const int nxcls = (live && idx + 1 < hi_cut) ? ec[idx + 1] : -2;
+                    const unsigned endbits = __ballot_sync(0xffffffffu, live && nxcls != mycls);
+                    const int nlive = hi_cut - blk < 32 ? hi_cut - blk : 32;
+#pragma unroll
+                    for (int e0 = 0; e0 < 32; e0 += 8) {
+                        if (e0 >= nlive) break;
+                        float xv[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const uint32_t ad = tg_lane + (uint32_t)__shfl_sync(0xffffffffu, myoff, e0 + e);   // dead lanes: row 0, unused
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[e]) : "r"(ad));
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (e0 + e < nlive) {
+                                s1 += xv[e];
+                                s2 = fmaf(xv[e], xv[e], s2);
+                                if ((endbits >> (e0 + e)) & 1u) {
+                                    const int k = __shfl_sync(0xffffffffu, mycls, e0 + e);
+                                    a1[(size_t)k * D] += s1;
+                                    a2[(size_t)k * D] += s2;
+                                    s1 = 0.f;
+                                    s2 = 0.f;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (prof) dbg[3] += clock64() - t_seg0;
+                named_bar_sync(gbar, 128);          // the group is done reading its tile
+                if (q + kTcGroups >= total_chunks || (q + kTcGroups) / NB != t) {   // last chunk of this tile for the group
+                    if (lane == 0) mbar_arrive(sort_free(par));
+                }
+            }
         }
     } else if (warp == kTcMmaWarp) {
         // =========================== MMA issuer ========================================
@@ -343,9 +389,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + kAccCol0 + (uint32_t)par * 32;
                 for (int b = 0; b < NB; ++b) {
-                    const long long q = (long long)t * NB + b;
-                    const int stage = (int)(q & 3);
-                    const uint32_t use = (uint32_t)(q >> 2);
+                    const int q = t * NB + b;
+                    const int stage = q & 3;
+                    const uint32_t use = (uint32_t)q >> 2;
                     mbar_wait_t(full_a(stage), use & 1, prof, dbg[1]);
                     tc_fence_after();
 #pragma unroll
@@ -405,26 +451,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const int ew = et >> 5;
 #pragma unroll
             for (int s = 0; s < kStatSlots; ++s) {
-                const float x = warp_sum(v[s]);
-                if (lane == 0) red[ew * kStatSlots + s] = x;
+                const float xs = warp_sum(v[s]);
+                if (lane == 0) red[ew * kStatSlots + s] = xs;
             }
             named_bar_sync(2, 128);
             if (et < kStatSlots) {
-                float x = 0.f;
-                for (int w = 0; w < 4; ++w) x += red[w * kStatSlots + et];
-                p.stat_partials[(size_t)blockIdx.x * kStatSlots + et] = x;
+                float xs = 0.f;
+                for (int w = 0; w < 4; ++w) xs += red[w * kStatSlots + et];
+                p.stat_partials[(size_t)blockIdx.x * kStatSlots + et] = xs;
             }
         }
-    } else if (SUMS && warp >= kTcSumWarp0 && warp < kTcSumWarp0 + 4) {
-        // =========================== class sums ==========================================
-        // Per tile the four warps first sort the 128 pixels by class (stable counting sort; class = first
-        // argmax of the EMA logits, prototype_handler.py:83-86).  Each staged chunk is then summed in that
-        // order: lane = channel, one running (sum, sum of squares) per class, at most one accumulator
-        // update per class and chunk -- the cost does not depend on how noisy the class map is, the
-        // summation order is fixed, and every accumulator has a single owner (no atomics).
-        const int sw = warp - kTcSumWarp0;
+    } else if (SUMS && warp >= kTcSortWarp0 && warp < kTcSortWarp0 + 4) {
+        // =========================== sorter ================================================
+        // Per tile: class of pixel 32*sw + lane = first argmax of the EMA logits (prototype_handler.py:83-86), then a
+        // stable counting sort of the 128 pixels by class (padding pixels form bucket 32, last).  Published per tile
+        // parity: row offset and class of every sorted entry, and the cuts of the sorted order into four ranges at
+        // class boundaries (one range per warp of a worker group).
+        const int sw = warp - kTcSortWarp0;
         float lv[CP];
-        auto fetch_logits = [&](int t) {   // the logits of tile t+1 are fetched while tile t is being summed
+        auto fetch_logits = [&](int t) {   // the logits of tile t+1 are fetched while tile t is being sorted
             const long long n = ((long long)blockIdx.x + (long long)t * gridDim.x) * kTilePixels + 32 * sw + lane;
             if (t < my_tiles && n < p.N) load_pixel_row<CP>(p.logits, C, HW, n, lv);
         };
@@ -433,12 +478,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         for (int t = 0; t < my_tiles; ++t) {
             const int par = t & 1;
             const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-            int* permp = perm + par * kTilePixels;
-            int* sclsp = scls + par * kTilePixels;
-            int* wc = wcnt + par * 4 * 36;
-            int* offp = coffs + par * 36;
-            const long long t_ys0 = prof ? clock64() : 0;
-            // ---- stable counting sort of the tile's pixels by class (padding pixels form bucket 32, last)
             const long long n = tile * kTilePixels + 32 * sw + lane;
             const int y = (n < p.N) ? first_argmax<CP>(lv, C) : -1;
             const int bucket = y < 0 ? 32 : y;
@@ -448,7 +487,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             if (lane < 4) wc[sw * 36 + 32 + lane] = 0;
             __syncwarp();
             if ((peers & lt_mask) == 0) wc[sw * 36 + bucket] = __popc(peers);      // lowest lane of each class present
-            if (prof) { const long long t0 = clock64(); named_bar_sync(1, 128); dbg[1] += clock64() - t0; } else named_bar_sync(1, 128);
+            named_bar_sync(1, 128);
             // lane l: size of class l over the tile, then an exclusive prefix over classes
             const int tot = wc[lane] + wc[36 + lane] + wc[72 + lane] + wc[108 + lane];
             int incl = tot;
@@ -458,68 +497,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 if (lane >= o) incl += v;
             }
             const int n_valid = __shfl_sync(0xffffffffu, incl, 31);
-            const unsigned present = __ballot_sync(0xffffffffu, tot > 0 && lane < C);   // classes with pixels in this tile
-            if (sw == 0) {
-                offp[lane] = incl - tot;
-                if (lane == 31) offp[32] = incl;
-            }
-            // this warp's share of the sorted order: the classes whose run starts in [lo, hi), with the cuts at the
-            // first class boundary at or after entries 32, 64 and 96
             const int cstart = incl - tot;
-            const bool has = tot > 0 && lane < C;
-            const int lo_cut = sw == 0 ? 0 : (int)__reduce_min_sync(0xffffffffu, (unsigned)((has && cstart >= 32 * sw) ? cstart : n_valid));
-            const int hi_cut = sw == 3 ? kTilePixels + 1 : (int)__reduce_min_sync(0xffffffffu, (unsigned)((has && cstart >= 32 * (sw + 1)) ? cstart : n_valid + 1));
-            const unsigned mine = __ballot_sync(0xffffffffu, has && cstart >= lo_cut && cstart < hi_cut);
-            int base = __shfl_sync(0xffffffffu, incl - tot, bucket & 31);
+            int base = __shfl_sync(0xffffffffu, cstart, bucket & 31);
             if (bucket == 32) base = n_valid;
             for (int w2 = 0; w2 < sw; ++w2) base += wc[w2 * 36 + bucket];
             const int pos = base + __popc(peers & lt_mask);
-            sclsp[pos] = y;
-            if (sw == 0 && lane < C) cnt[lane] += tot;                               // pixel counts per class
-            named_bar_sync(1, 128);
-            // sorted entry -> row offset of its pixel; sclsp holds the class of each sorted entry (-1 = padding)
-            {
-                permp[pos] = (32 * sw + lane) * (kTcTRow * 4);      // byte offset of the pixel's row in a class-sum tile
+            // cut r = first class boundary at or after entry 32*r
+            const bool has = tot > 0 && lane < C;
+            const int my_cut = sw == 0 ? 0 : (int)__reduce_min_sync(0xffffffffu, (unsigned)((has && cstart >= 32 * sw) ? cstart : n_valid));
+            if (t >= 2) mbar_wait_t(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // workers are done with tile t-2
+            eoff[par * kTilePixels + pos] = (32 * sw + lane) * (kTcTRow * 4);
+            ecls[par * kTilePixels + pos] = y;
+            if (lane == 0) {
+                cuts[par * 8 + sw] = my_cut;
+                if (sw == 3) cuts[par * 8 + 4] = n_valid;
             }
-            named_bar_sync(1, 128);
-            if (prof) dbg[4] += clock64() - t_ys0;
-
-            const int pairs = NB / 2;
-            for (int j = 0; j < pairs; ++j) {
-                const int pair = t * pairs + j, tstage = pair & 1;
-                mbar_wait_t(full_t(tstage), ((uint32_t)pair >> 1) & 1, prof, dbg[0]);
-                const long long t_seg0 = prof ? clock64() : 0;
-                // lane = channels (64j + 2*lane, +1).  One pass per class of this warp's range (warp-uniform mask):
-                // packed (sum, sum of squares) over the class's run of sorted entries, then one accumulator update.
-                const uint32_t rowbase = smem_u32(Tst + (size_t)tstage * kTilePixels * kTcTRow) + 8u * lane;
-                const uint32_t a1 = smem_u32(acc) + 4u * (64 * j + 2 * lane);
-                const uint32_t a2 = a1 + 4u * C * D;
-                unsigned todo = mine;
-                while (todo) {
-                    const int k = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    int i = offp[k];
-                    const int i1 = offp[k + 1];
-                    uint64_t s1 = 0, s2 = 0;
-                    for (; i + 4 <= i1; i += 4) {
-                        const uint64_t x0 = lds64(rowbase + permp[i]), x1 = lds64(rowbase + permp[i + 1]);
-                        const uint64_t x2 = lds64(rowbase + permp[i + 2]), x3 = lds64(rowbase + permp[i + 3]);
-                        s1 = fadd2(s1, fadd2(fadd2(x0, x1), fadd2(x2, x3)));
-                        s2 = fadd2(s2, fadd2(ffma2(x0, x0, fmul2(x1, x1)), ffma2(x2, x2, fmul2(x3, x3))));
-                    }
-                    for (; i < i1; ++i) {
-                        const uint64_t x0 = lds64(rowbase + permp[i]);
-                        s1 = fadd2(s1, x0);
-                        s2 = ffma2(x0, x0, s2);
-                    }
-                    const uint32_t off = 4u * k * D;
-                    sts64(a1 + off, fadd2(lds64(a1 + off), s1));
-                    sts64(a2 + off, fadd2(lds64(a2 + off), s2));
-                }
-                if (prof) dbg[2] += clock64() - t_seg0;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty_t(tstage));
-            }
+            if (sw == 0 && lane < C) cnt[lane] += tot;          // pixel counts per class
+            mbar_arrive(sort_ready(par));
+            named_bar_sync(1, 128);                              // wc is reused by the next tile
         }
     }
 

@@ -21,8 +21,8 @@ torch.cuda.synchronize()
 lib.onda_debug_set_buffer(None)
 d = buf.view(148, 32, 8).double().cpu()
 tot = d[:, :, 7]
-names = {"loader": (0, 16, ["wait acc_empty", "wait empty_t(summer)", "wait empty_a(mma)", "wait global loads"]),
-         "epilogue": (16, 20, ["wait acc_full"]), "summer": (20, 24, ["wait full_t", "ys barrier", "summation loops", "-", "sort phase"]),
+names = {"worker": (0, 16, ["wait acc_empty", "wait sort_ready", "wait empty_a(mma)", "class-sum phase"]),
+         "epilogue": (16, 20, ["wait acc_full"]), "sorter": (20, 24, ["wait sort_free"]),
          "mma": (24, 25, ["wait acc_empty", "wait full_a"])}
 print("mean total cycles per warp:", tot[:, :25].mean().item())
 for role, (a, b, labels) in names.items():
