@@ -48,10 +48,15 @@ struct PixelStats {
 // Loads the C logits of pixel n (NCHW, coalesced across a warp) with every load in flight at once.
 template <int CP>
 __device__ __forceinline__ void load_pixel_row(const float* base, int C, int HW, long long n, float (&v)[CP]) {
-    const long long b = n / HW, q = n - b * HW;
-    const float* lp = base + (b * C) * (long long)HW + q;
+    const unsigned nu = (unsigned)n, hw = (unsigned)HW;
+    const unsigned b = nu / hw, q = nu - b * hw;
+    const char* lp = reinterpret_cast<const char*>(base + ((size_t)b * C) * hw + q);
+    const size_t plane = (size_t)hw * sizeof(float);
 #pragma unroll
-    for (int k = 0; k < CP; ++k) v[k] = (k < C) ? __ldg(lp + (long long)k * HW) : 0.f;
+    for (int k = 0; k < CP; ++k) {
+        v[k] = (k < C) ? __ldg(reinterpret_cast<const float*>(lp)) : 0.f;
+        lp += plane;
+    }
 }
 
 // First maximal index with torch semantics (prototype_handler.onehot, prototype_handler.py:83-86).
@@ -65,11 +70,12 @@ __device__ __forceinline__ int first_argmax(const float (&v)[CP], int C) {
     return arg;
 }
 
-// ---- fast single-instruction math (MUFU): relative error ~2^-22, far inside the 1e-5 parity budget
-__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// ---- fast single-instruction math (MUFU, flush-to-zero forms: no denormal fix-up code): relative error ~2^-22,
+// far inside the 1e-5 parity budget; a flushed denormal only ever replaces a value below 1.2e-38 by 0
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // Everything after the squared distances for one pixel (one thread).  Follows
 // prototype_handler.pseudo_labels (prototype_handler.py:140-166) step by step:

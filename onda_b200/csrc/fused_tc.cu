@@ -6,7 +6,7 @@
 //     x' . Q  =  hi(x').hi(Q) + hi(x').lo(Q) + lo(x').hi(Q)      (fp32 accumulate in TMEM)
 // which keeps fp32-level accuracy (the dropped lo.lo term is 2^-22 relative).
 //
-// One persistent CTA per SM, 25 warps, over a single global chunk sequence (chunk = 128 pixels x
+// One persistent CTA per SM, 24 warps, over a single global chunk sequence (chunk = 128 pixels x
 // 32 channels; a tile of 128 pixels is D/32 consecutive chunks):
 //   warps  0-15  workers, four groups of four; warp w%4 is the pixel quarter (the only TMEM lanes a warp
 //                may touch are 32*(w%4)..+31), w/4 the group; group g takes chunks g, g+4, g+8, ...
@@ -20,9 +20,9 @@
 //                chunk: fixed summation order, no atomics.
 //   warps 16-19  epilogue: tcgen05.ld of the 32 accumulator columns of their pixel, then the common
 //                per-pixel tail (epilogue.cuh): sqrt, softmax, prior rectification, label, statistics.
-//   warps 20-23  sorter: per tile, class of every pixel (first argmax of the EMA logits) and a stable
+//   warps 20-21  sorter: per tile, class of every pixel (first argmax of the EMA logits) and a stable
 //                counting sort of the 128 pixels by class, published for the workers (double-buffered).
-//   warp   24    MMA issuer: per chunk 4 K-steps x 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
+//   warp   22    MMA issuer: per chunk 4 K-steps x 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
 //                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory.
 // Every mbarrier has one producer side and one consumer side that visit it phase by phase, in order.
 // Two accumulator buffers of 32 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
@@ -32,9 +32,9 @@ namespace onda {
 
 constexpr int kTcWorkerWarps = 16;
 constexpr int kTcEpiWarp0 = 16;
-constexpr int kTcSortWarp0 = 20;
-constexpr int kTcMmaWarp = 24;
-constexpr int kTcThreads = 25 * 32;
+constexpr int kTcSortWarp0 = 20;                 // two sorter warps, two pixels per lane
+constexpr int kTcMmaWarp = 22;                   // warp 23 is idle: 24 warps = six full warpgroups -> 80 registers per thread
+constexpr int kTcThreads = 24 * 32;
 constexpr int kTcGroups = 4;                     // worker groups = TMEM A stages = class-sum tiles
 constexpr int kTcChunkC = 32;                    // channels per chunk
 constexpr int kTcTRow = 34;                      // floats per pixel row of a class-sum tile: 32 channels + 2 (conflict-free STS.64 and LDS.32)
@@ -62,22 +62,23 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Wait with exponential back-off: up to ~20 of the 25 warps of the CTA are waiting at any moment, and
-// tight polling floods the shared-memory pipeline that the working warps need for LDS/STS.
+// Wait with a fixed sleep between probes.  Polling costs issue slots and shared-memory pipeline slots that the
+// working warps need, so roles that wait for long events (epilogue, sorter) pass a long sleep.
+template <int kSleepNs = 64>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
-    uint32_t ns = 32, tries = 0;
+    uint32_t tries = 0;
     while (!mbar_try(bar, parity)) {
-        __nanosleep(ns);
-        if (ns < 256) ns <<= 1;
+        __nanosleep(kSleepNs);
         if (++tries > kSpinLimit) __trap();   // a stuck pipeline traps instead of hanging the GPU
     }
 }
 // wait that adds its duration to a diagnostic counter when profiling is on
+template <int kSleepNs = 64>
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, long long& acc_cycles) {
-    if (!prof) { mbar_wait(bar, parity); return; }
+    if (!prof) { mbar_wait<kSleepNs>(bar, parity); return; }
     const long long t0 = clock64();
-    mbar_wait(bar, parity);
+    mbar_wait<kSleepNs>(bar, parity);
     acc_cycles += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -186,12 +187,13 @@ __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     return s;
 }
 
-template <int CP, bool SUMS, bool WANT_DIST>
+template <int CP, bool SUMS, bool WANT_DIST, bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = p.C, D = p.D, HW = p.HW;
     const int NB = D / kTcChunkC;
+    const int nb_shift = NB == 8 ? 3 : 2;              // D = 256 or 128 (tc_supported)
     const TcSmem L = tc_smem(D, C, CP, SUMS);
     float* Bhi = reinterpret_cast<float*>(smem_raw + L.bhi);
     float* Blo = reinterpret_cast<float*>(smem_raw + L.blo);
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         for (int i = 0; i < 2; ++i) {
             mbar_init(acc_full(i), 1);
             mbar_init(acc_empty(i), 128);
-            mbar_init(sort_ready(i), 128);
+            mbar_init(sort_ready(i), 64);
             mbar_init(sort_free(i), kTcWorkerWarps);
         }
         fence_barrier_init();
@@ -253,9 +255,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const bool prof = p.debug != nullptr;
+    constexpr bool prof = PROF;       // per-warp wait counters (onda_debug_set_buffer); compiled out of the production kernel
     long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long t_start = clock64();
+    const long long t_start = PROF ? clock64() : 0;
     const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_chunks = my_tiles * NB;
     const unsigned HWu = (unsigned)HW, Nu = (unsigned)p.N;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         const int gbar = 3 + group;                                   // named barrier of the group (128 threads)
         float x[kTcChunkC];
         auto issue_loads = [&](int q) {
-            const int t = q / NB, b = q - t * NB;
+            const int t = q >> nb_shift, b = q & (NB - 1);
             const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
             unsigned n = tile * kTilePixels + 32 * quarter + lane;
             n = n < Nu ? n : Nu - 1;         // clamp: results of padded rows are never stored (epilogue / sorter guard them)
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         };
         if (group < total_chunks) issue_loads(group);
         for (int q = group; q < total_chunks; q += kTcGroups) {
-            const int t = q / NB, b = q - t * NB;
+            const int t = q >> nb_shift, b = q & (NB - 1);
             const int par = t & 1;
             const uint32_t use = (uint32_t)q >> 2;
             if (SUMS) {   // raw values into the group's tile, pixel-major, two channels per 8-byte store
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 }
                 if (prof) dbg[3] += clock64() - t_seg0;
                 named_bar_sync(gbar, 128);          // the group is done reading its tile
-                if (q + kTcGroups >= total_chunks || (q + kTcGroups) / NB != t) {   // last chunk of this tile for the group
+                if (q + kTcGroups >= total_chunks || ((q + kTcGroups) >> nb_shift) != t) {   // last chunk of this tile for the group
                     if (lane == 0) mbar_arrive(sort_free(par));
                 }
             }
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                     for (int k = 0; k < CP; ++k) pri[k] = 0.f;
                 }
             }
-            mbar_wait_t(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
+            mbar_wait_t<400>(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
             tc_fence_after();
             uint32_t dv[32];
             tc_ld32(tmem_base + lane_base + kAccCol0 + (uint32_t)par * 32, dv);
@@ -461,65 +463,83 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 p.stat_partials[(size_t)blockIdx.x * kStatSlots + et] = xs;
             }
         }
-    } else if (SUMS && warp >= kTcSortWarp0 && warp < kTcSortWarp0 + 4) {
+    } else if (SUMS && warp >= kTcSortWarp0 && warp < kTcSortWarp0 + 2) {
         // =========================== sorter ================================================
-        // Per tile: class of pixel 32*sw + lane = first argmax of the EMA logits (prototype_handler.py:83-86), then a
-        // stable counting sort of the 128 pixels by class (padding pixels form bucket 32, last).  Published per tile
-        // parity: row offset and class of every sorted entry, and the cuts of the sorted order into four ranges at
-        // class boundaries (one range per warp of a worker group).
+        // Per tile: class of every pixel = first argmax of the EMA logits (prototype_handler.py:83-86), then a stable
+        // counting sort of the 128 pixels by class (padding pixels form bucket 32, last).  Two warps, two pixels per
+        // lane: "virtual warp" v = 2*sw + r owns pixels 32*v .. 32*v+31.  Published per tile parity: row offset and
+        // class of every sorted entry, and the cuts of the sorted order into four ranges at class boundaries (one
+        // range per warp of a worker group).
         const int sw = warp - kTcSortWarp0;
-        float lv[CP];
+        float lv[2][CP];
         auto fetch_logits = [&](int t) {   // the logits of tile t+1 are fetched while tile t is being sorted
-            const long long n = ((long long)blockIdx.x + (long long)t * gridDim.x) * kTilePixels + 32 * sw + lane;
-            if (t < my_tiles && n < p.N) load_pixel_row<CP>(p.logits, C, HW, n, lv);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const long long n = ((long long)blockIdx.x + (long long)t * gridDim.x) * kTilePixels + 32 * (2 * sw + r) + lane;
+                if (t < my_tiles && n < p.N) load_pixel_row<CP>(p.logits, C, HW, n, lv[r]);
+            }
         };
         fetch_logits(0);
         const unsigned lt_mask = (1u << lane) - 1u;
         for (int t = 0; t < my_tiles; ++t) {
             const int par = t & 1;
             const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-            const long long n = tile * kTilePixels + 32 * sw + lane;
-            const int y = (n < p.N) ? first_argmax<CP>(lv, C) : -1;
-            const int bucket = y < 0 ? 32 : y;
+            int y[2], bucket[2];
+            unsigned peers[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int v = 2 * sw + r;
+                const long long n = tile * kTilePixels + 32 * v + lane;
+                y[r] = (n < p.N) ? first_argmax<CP>(lv[r], C) : -1;
+                bucket[r] = y[r] < 0 ? 32 : y[r];
+                peers[r] = __match_any_sync(0xffffffffu, bucket[r]);
+                wc[v * 36 + lane] = 0;
+                if (lane < 4) wc[v * 36 + 32 + lane] = 0;
+                __syncwarp();
+                if ((peers[r] & lt_mask) == 0) wc[v * 36 + bucket[r]] = __popc(peers[r]);   // lowest lane of each class present
+            }
             fetch_logits(t + 1);
-            const unsigned peers = __match_any_sync(0xffffffffu, bucket);
-            wc[sw * 36 + lane] = 0;
-            if (lane < 4) wc[sw * 36 + 32 + lane] = 0;
-            __syncwarp();
-            if ((peers & lt_mask) == 0) wc[sw * 36 + bucket] = __popc(peers);      // lowest lane of each class present
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 64);
             // lane l: size of class l over the tile, then an exclusive prefix over classes
             const int tot = wc[lane] + wc[36 + lane] + wc[72 + lane] + wc[108 + lane];
             int incl = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+                const int vv = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += vv;
             }
             const int n_valid = __shfl_sync(0xffffffffu, incl, 31);
             const int cstart = incl - tot;
-            int base = __shfl_sync(0xffffffffu, cstart, bucket & 31);
-            if (bucket == 32) base = n_valid;
-            for (int w2 = 0; w2 < sw; ++w2) base += wc[w2 * 36 + bucket];
-            const int pos = base + __popc(peers & lt_mask);
-            // cut r = first class boundary at or after entry 32*r
             const bool has = tot > 0 && lane < C;
-            const int my_cut = sw == 0 ? 0 : (int)__reduce_min_sync(0xffffffffu, (unsigned)((has && cstart >= 32 * sw) ? cstart : n_valid));
-            if (t >= 2) mbar_wait_t(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // workers are done with tile t-2
-            eoff[par * kTilePixels + pos] = (32 * sw + lane) * (kTcTRow * 4);
-            ecls[par * kTilePixels + pos] = y;
-            if (lane == 0) {
-                cuts[par * 8 + sw] = my_cut;
-                if (sw == 3) cuts[par * 8 + 4] = n_valid;
+            // cut c = first class boundary at or after entry 32*c (c = 1..3)
+            int cut[4];
+            cut[0] = 0;
+#pragma unroll
+            for (int c = 1; c < 4; ++c)
+                cut[c] = (int)__reduce_min_sync(0xffffffffu, (unsigned)((has && cstart >= 32 * c) ? cstart : n_valid));
+            if (t >= 2) mbar_wait_t<400>(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // workers are done with tile t-2
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int v = 2 * sw + r;
+                int base = __shfl_sync(0xffffffffu, cstart, bucket[r] & 31);
+                if (bucket[r] == 32) base = n_valid;
+                for (int v2 = 0; v2 < v; ++v2) base += wc[v2 * 36 + bucket[r]];
+                const int pos = base + __popc(peers[r] & lt_mask);
+                eoff[par * kTilePixels + pos] = (32 * v + lane) * (kTcTRow * 4);
+                ecls[par * kTilePixels + pos] = y[r];
             }
-            if (sw == 0 && lane < C) cnt[lane] += tot;          // pixel counts per class
+            if (sw == 0) {
+                if (lane < 4) cuts[par * 8 + lane] = lane == 0 ? 0 : (lane == 1 ? cut[1] : (lane == 2 ? cut[2] : cut[3]));
+                if (lane == 4) cuts[par * 8 + 4] = n_valid;
+                if (lane < C) cnt[lane] += tot;                  // pixel counts per class
+            }
             mbar_arrive(sort_ready(par));
-            named_bar_sync(1, 128);                              // wc is reused by the next tile
+            named_bar_sync(1, 64);                               // wc is reused by the next tile
         }
     }
 
     // ---- teardown: publish the class partials, release tensor memory
-    if (prof && lane == 0) {
+    if (PROF && p.debug != nullptr && lane == 0) {
         long long* d = p.debug + ((size_t)blockIdx.x * 32 + warp) * 8;
         dbg[7] = clock64() - t_start;
         for (int i = 0; i < 8; ++i) d[i] = dbg[i];
@@ -546,9 +566,9 @@ bool tc_supported(int B, int D, int HW, int C) {
 
 int tc_grid(int tiles, int sms) { return tiles < sms ? tiles : sms; }
 
-template <int CP, bool SUMS, bool WANT_DIST>
+template <int CP, bool SUMS, bool WANT_DIST, bool PROF>
 static int launch_tc(const FusedParams& p, int grid, cudaStream_t stream) {
-    auto kern = fused_tc_kernel<CP, SUMS, WANT_DIST>;
+    auto kern = fused_tc_kernel<CP, SUMS, WANT_DIST, PROF>;
     const size_t smem = tc_smem(p.D, p.C, CP, SUMS).total;
     ONDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     timing_begin(stream);
@@ -562,8 +582,9 @@ static int launch_tc(const FusedParams& p, int grid, cudaStream_t stream) {
 template <int CP>
 static int launch_tc_cp(const FusedParams& p, int grid, bool sums, cudaStream_t stream) {
     const bool dist = p.dist != nullptr;
-    if (sums) return dist ? launch_tc<CP, true, true>(p, grid, stream) : launch_tc<CP, true, false>(p, grid, stream);
-    return dist ? launch_tc<CP, false, true>(p, grid, stream) : launch_tc<CP, false, false>(p, grid, stream);
+    if (p.debug != nullptr && sums && !dist) return launch_tc<CP, true, false, true>(p, grid, stream);   // diagnostics build
+    if (sums) return dist ? launch_tc<CP, true, true, false>(p, grid, stream) : launch_tc<CP, true, false, false>(p, grid, stream);
+    return dist ? launch_tc<CP, false, true, false>(p, grid, stream) : launch_tc<CP, false, false, false>(p, grid, stream);
 }
 
 int launch_fused_tc(const FusedParams& p, int grid, bool sums, cudaStream_t stream) {
