@@ -156,12 +156,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(d, n_gpus):
+def workload_config(d, n_gpus, allreduce="oneshot"):
     return {"workload": (f"BASELINE configs[2]: batch-sharded prototype path, B={B_PER_GPU} images per GPU at 1024x512 "
                          f"(65x129 stride-8 map), D={d}, C={C}, mahalanobis, hybrid_switch.yml parameters; step = fused "
                          "hard+soft pseudo-labels + class sum/sumsq/count + statistics + EMA update"),
             "B_per_gpu": B_PER_GPU, "D": d, "H": H, "W": W, "classes": C, "parallelism": f"batch-sharded x{n_gpus}",
-            "collective": "all-reduce of 19x(2D+1)+8 floats per step" if n_gpus > 1 else "none",
+            "collective": f"{allreduce} all-reduce of 19x(2D+1)+8 floats per step" if n_gpus > 1 else "none",
             "l2_policy": "inputs larger than L2 (338 MB per step at D=256) and two rotating input sets"}
 
 
@@ -190,7 +190,7 @@ def run_onda(args):
     if world > 1:   # identical prototypes everywhere
         for t in (protos, sq_mean, counter):
             dist.broadcast(t, 0)
-    h = prototype_handler(process_group=group, impl=args.kernel, **PARAMS)
+    h = prototype_handler(process_group=group, impl=args.kernel, allreduce=args.allreduce, **PARAMS)
     h.prototypes, h.squared_mean, h.counter = protos.clone(), sq_mean.clone(), counter.clone()
 
     def step(i):
@@ -292,7 +292,7 @@ def run_onda(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(d, world),
+        "dtype": "f32", "data": "synthetic", "config": workload_config(d, world, args.allreduce),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps},
@@ -322,6 +322,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="onda", choices=["onda", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--allreduce", default="oneshot", choices=["nccl", "oneshot"],
+                    help="exchange of the class-sum buffer at N>1: NCCL all_reduce or the library's one-shot NVLink kernel")
     ap.add_argument("--d", type=int, default=256, help="feature width (256 = real ProDA head, 2048 = stress size)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -94,7 +94,8 @@ int onda_impl_supported(int B, int D, int HW, int C, int impl);
  * point, the scaled prototypes Q = w*(P-mu) and the per-class bias
  * sum_j w_j (P_kj-mu_j)^2, so that d^2[n,k] = sum_j w_j (x_nj-mu_j)^2 - 2 (x_n-mu).Q_k + bias_k
  * equals the reference's sum_j ((x_nj-P_kj)/sigma_j)^2 (prototype_handler.py:117-120, :132-135).
- * `squared_mean` and `counter` may be NULL for ONDA_METRIC_EUCLIDEAN.
+ * `squared_mean` and `counter` may be NULL for ONDA_METRIC_EUCLIDEAN.  The table buffer (onda_table_floats floats)
+ * must be zero-initialised before its first use (it holds a ticket counter that the kernel re-arms itself).
  */
 int onda_build_distance_table(const float* prototypes, const float* squared_mean, const float* counter,
                               int C, int D, int metric, float* table, void* stream);
@@ -126,6 +127,10 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
  * squared mean; counter untouched.  prototype_handler.py:88-99. */
 int onda_ema_update(float* prototypes, float* squared_mean, const float* sums, int C, int D, float ma_lambda,
                     void* stream);
+/* ma() and the rebuild of the distance table for the next step in ONE launch (same results as onda_ema_update
+ * followed by onda_build_distance_table; `table` must have been zero-initialised once, like for the plain build). */
+int onda_ema_update_and_table(float* prototypes, float* squared_mean, const float* counter, const float* sums, int C,
+                              int D, float ma_lambda, int metric, float* table, void* stream);
 /* append(): counter += cnt; P += (sum - P*cnt)/max(counter,1); likewise S.  prototype_handler.py:62-74. */
 int onda_append_update(float* prototypes, float* squared_mean, float* counter, const float* sums, int C, int D,
                        void* stream);
@@ -146,14 +151,17 @@ size_t onda_prior_workspace_bytes(int B, int C, int HW);
 
 /* ---- multi-GPU ---------------------------------------------------------------- */
 /*
- * One-shot sum all-reduce of `n` floats over `world` ranks whose buffers are mapped into this
- * process (NVLink peer memory).  peer_bufs[r] / peer_flags[r] are DEVICE-visible pointers to rank
- * r's staging buffer (n floats) and flag word; every rank pushes nothing and instead reads all
- * peers' staging buffers in rank order 0..world-1 after a flag handshake, so every rank computes
- * bit-identical sums.  `local` (n floats) is this rank's input and receives the result.
- * Replaces nothing in the reference (it is single-GPU); see DESIGN.md section (e).
+ * One-shot sum all-reduce of `n` floats over `world` <= 8 ranks of one NVLink/NVSwitch node.
+ * peer_bufs_host[r] / peer_flags_host[r] (HOST arrays of `world` DEVICE pointers) are rank r's input buffer
+ * (n floats) and flag array (`world` uint32, zero-initialised) as mapped into this process (symmetric / peer
+ * memory); this rank's own input is peer_bufs_host[rank].  The kernel stores `epoch` (non-zero, increasing,
+ * the same on every rank for a given call) into flag[rank] of every peer, waits for all `world` flags of its
+ * own array, then every rank reads all inputs and adds them in rank order 0..world-1 into `out` (local memory,
+ * n floats): all ranks obtain bit-identical sums.  Inputs must be double-buffered by the caller (two slots
+ * with separate flag arrays, alternating per call).  Replaces nothing in the reference (single GPU); it is the
+ * exchange step of the batch-sharded path, DESIGN.md section (e).
  */
-int onda_allreduce_oneshot(float* local, size_t n, int rank, int world, void* const* peer_bufs_host,
+int onda_allreduce_oneshot(float* out, size_t n, int rank, int world, void* const* peer_bufs_host,
                            void* const* peer_flags_host, uint32_t epoch, void* stream);
 
 #ifdef __cplusplus

@@ -59,87 +59,112 @@ static int cached_sm_count() {
     return sms;
 }
 
-// ---- distance table ----------------------------------------------------------------------
-// One CTA: the whole state is C*D <= 32*4096 floats.  All reductions are fixed-order.
-constexpr int kTableThreads = 256;
+// ---- distance table (optionally fused with the EMA blend) ---------------------------------------
+// One warp-sized CTA per 32 channels, thread = channel: every quantity of the table is per channel except the
+// per-class bias, whose per-CTA partial sums are folded by the last CTA to finish, in CTA order (deterministic).
+// With `sums` != null the moving-average blend of ma() (prototype_handler.py:88-99) is applied to P and S first,
+// in the same thread that then rebuilds the channel's table entries.
+constexpr int kTableThreads = 32;
 
-__global__ void __launch_bounds__(kTableThreads) table_kernel(const float* __restrict__ P, const float* __restrict__ S,
+__global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict__ P, float* __restrict__ S,
                                                               const float* __restrict__ cnt, int C, int D, int metric,
-                                                              float* __restrict__ table) {
+                                                              float* __restrict__ table, const float* __restrict__ sums,
+                                                              float lam) {
     const TableLayout T = table_layout(C, D);
-    __shared__ double bias_part[kTableThreads / 32][32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x;
+    const int j = blockIdx.x * kTableThreads + lane;
     const bool mahal = metric == ONDA_METRIC_MAHALANOBIS;
-    double total = 0.0;
-    if (mahal)
-        for (int k = 0; k < C; ++k) total += (double)cnt[k];
+    __shared__ double wk[32];              // c_k / sum_k c_k
+    {
+        double ck = (mahal && lane < C) ? (double)cnt[lane] : 0.0, total = ck;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        wk[lane] = ck / total;
+    }
+    __syncwarp();
     double b[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) b[k] = 0.0;
-    for (int j = tid; j < T.Dp; j += kTableThreads) {
-        float sigma = 0.f, wf = 0.f, muf = 0.f;
-        if (j < D) {
-            double gm = 0.0, gsq = 0.0, mean = 0.0;
-            for (int k = 0; k < C; ++k) {
-                const double pk = (double)P[(size_t)k * D + j];
-                mean += pk;
+    float pk[32];
+    float sigma = 0.f, wf = 0.f, muf = 0.f;
+    if (j < D) {
+        double gm = 0.0, gsq = 0.0, mean = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            pk[k] = 0.f;
+            if (k < C) {
+                float pv = P[(size_t)k * D + j];
+                float sv = (mahal || sums != nullptr) ? S[(size_t)k * D + j] : 0.f;
+                if (sums != nullptr) {     // ma(): P <- P*rho + (1-rho)*sum/max(cnt,1), rho = lambda if cnt > 0 else 1
+                    const float n = sums[(size_t)2 * C * D + k];
+                    const float rho = n > 0.f ? lam : 1.f;
+                    const float one_m = __fsub_rn(1.f, rho);
+                    const float den = n > 0.f ? n : 1.f;
+                    pv = __fadd_rn(__fmul_rn(pv, rho), __fmul_rn(one_m, __fdiv_rn(sums[(size_t)k * D + j], den)));
+                    sv = __fadd_rn(__fmul_rn(sv, rho), __fmul_rn(one_m, __fdiv_rn(sums[(size_t)(C + k) * D + j], den)));
+                    P[(size_t)k * D + j] = pv;
+                    S[(size_t)k * D + j] = sv;
+                }
+                pk[k] = pv;
+                mean += (double)pv;
                 if (mahal) {
-                    const double ck = (double)cnt[k];
-                    gm += pk * ck / total;                          // global_var(): prototype_handler.py:57-59
-                    gsq += (double)S[(size_t)k * D + j] * ck / total;  // :54-56
+                    gm += (double)pv * wk[k];          // global_var(): prototype_handler.py:57-59
+                    gsq += (double)sv * wk[k];         // :54-56
                 }
             }
-            if (mahal) {
-                sigma = (float)sqrt(gsq - gm * gm);                  // :60
-                wf = (float)(1.0 / ((double)sigma * (double)sigma));
-                muf = (float)gm;
-            } else {
-                sigma = 1.f;
-                wf = 1.f;
-                muf = (float)(mean / C);
-            }
         }
+        if (mahal) {
+            sigma = (float)sqrt(gsq - gm * gm);        // :60
+            wf = (float)(1.0 / ((double)sigma * (double)sigma));
+            muf = (float)gm;
+        } else {
+            sigma = 1.f;
+            wf = 1.f;
+            muf = (float)(mean / C);
+        }
+    }
+    if (j < T.Dp) {
         table[T.off_sigma + j] = sigma;
         table[T.off_w + j] = wf;
         table[T.off_mu + j] = muf;
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            if (k < T.CP) {
-                float qf = 0.f;
-                if (j < D && k < C) {
-                    const double diff = (double)P[(size_t)k * D + j] - (double)muf;
-                    qf = (float)((double)wf * diff);
-                    b[k] += (double)wf * diff * diff;
-                }
-                table[T.off_q + (size_t)j * T.CP + k] = qf;
+            float qf = 0.f;
+            if (j < D && k < C) {
+                const double diff = (double)pk[k] - (double)muf;
+                qf = (float)((double)wf * diff);
+                b[k] += (double)wf * diff * diff;
             }
+            if (k < T.CP) table[T.off_q + (size_t)j * T.CP + k] = qf;
+            // TF32 split of -2*Q in the tcgen05 B-operand layout (common.cuh); classes >= C are zero rows
+            const float v = -2.f * qf;
+            const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+            const size_t bi = (size_t)(j >> 2) * 128 + (size_t)k * 4 + (j & 3);
+            table[T.off_qhi + bi] = hi;
+            table[T.off_qlo + bi] = v - hi;
         }
     }
+    // per-class bias: warp sum of this CTA's channels, then the last CTA folds all CTAs in order
+    double* part = reinterpret_cast<double*>(table + T.off_scratch);
+    unsigned* ticket = reinterpret_cast<unsigned*>(table + T.off_scratch + (size_t)2 * 32 * gridDim.x);
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
         double v = b[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) bias_part[warp][k] = v;
+        if (lane == k) part[(size_t)blockIdx.x * 32 + k] = v;
     }
-    __syncthreads();
-    if (tid < 32) {
+    __threadfence();
+    __syncwarp();
+    unsigned last = 0;
+    if (lane == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        __threadfence();
         double v = 0.0;
-        for (int w = 0; w < kTableThreads / 32; ++w) v += bias_part[w][tid];
-        table[T.off_bias + tid] = (float)v;
-    }
-    // TF32 split of -2*Q in the tcgen05 B-operand layout (common.cuh); classes >= C are zero rows
-    __syncthreads();
-    for (int i = tid; i < 32 * T.Dp; i += kTableThreads) {
-        const int kc = i >> 7, n = (i >> 2) & 31, e = i & 3;
-        const int j = kc * 4 + e;
-        float v = 0.f;
-        if (n < C && n < T.CP) v = -2.f * table[T.off_q + (size_t)j * T.CP + n];
-        unsigned hbits;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hbits) : "f"(v));
-        const float hi = __uint_as_float(hbits);
-        table[T.off_qhi + i] = hi;
-        table[T.off_qlo + i] = v - hi;
+        for (unsigned c = 0; c < gridDim.x; ++c) v += __ldcg(part + (size_t)c * 32 + lane);
+        table[T.off_bias + lane] = (float)v;
+        if (lane == 0) *ticket = 0u;        // re-arm for the next build
     }
 }
 
@@ -166,8 +191,11 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     const int total = class_elems + kStatSlots;
     double s = 0.0;
     if (e < class_elems) {
-        if (has_sums)
-            for (int c = g; c < n_cta; c += 8) s += (double)cta_partials[(size_t)c * stride + e];
+        if (has_sums) {
+            const float* src = cta_partials + e;
+#pragma unroll 8
+            for (int c = g; c < n_cta; c += 8) s += (double)__ldcg(src + (size_t)c * stride);   // independent loads, one add chain
+        }
     } else if (e < total) {
         if (has_stats)
             for (int c = g; c < n_stat; c += 8) s += (double)stat_partials[(size_t)c * kStatSlots + (e - class_elems)];
@@ -312,6 +340,10 @@ __global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* _
 
 }  // namespace onda
 
+namespace onda {
+int launch_allreduce_oneshot(float* out, size_t n, int rank, int world, void* const* bufs, void* const* flags,
+                             uint32_t epoch, cudaStream_t stream);
+}
 using namespace onda;
 
 // =============================================================================================
@@ -404,7 +436,8 @@ int onda_build_distance_table(const float* prototypes, const float* squared_mean
                  "onda_build_distance_table: unexpected value for attribute distance_metric (%d)", metric);
     if (metric == ONDA_METRIC_MAHALANOBIS)
         ONDA_REQUIRE(squared_mean && counter, "onda_build_distance_table: mahalanobis needs squared_mean and counter");
-    table_kernel<<<1, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric, table);
+    table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(const_cast<float*>(prototypes), const_cast<float*>(squared_mean), counter, C, D, metric,
+                                                                                   table, nullptr, 0.f);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
@@ -501,6 +534,20 @@ int onda_ema_update(float* prototypes, float* squared_mean, const float* sums, i
     return ONDA_OK;
 }
 
+int onda_ema_update_and_table(float* prototypes, float* squared_mean, const float* counter, const float* sums, int C,
+                              int D, float ma_lambda, int metric, float* table, void* stream) {
+    ONDA_REQUIRE(prototypes && squared_mean && sums && table, "onda_ema_update_and_table: null pointer");
+    ONDA_REQUIRE(C > 0 && C <= ONDA_MAX_CLASSES && D > 0, "onda_ema_update_and_table: unsupported shape C=%d D=%d", C, D);
+    ONDA_REQUIRE(metric == ONDA_METRIC_EUCLIDEAN || metric == ONDA_METRIC_MAHALANOBIS,
+                 "onda_ema_update_and_table: unexpected value for attribute distance_metric (%d)", metric);
+    if (metric == ONDA_METRIC_MAHALANOBIS) ONDA_REQUIRE(counter, "onda_ema_update_and_table: mahalanobis needs counter");
+    table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
+                                                                                   table, sums, ma_lambda);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
 int onda_append_update(float* prototypes, float* squared_mean, float* counter, const float* sums, int C, int D,
                        void* stream) {
     ONDA_REQUIRE(prototypes && squared_mean && counter && sums && C > 0 && C <= ONDA_MAX_CLASSES && D > 0,
@@ -544,11 +591,14 @@ int onda_prior_mix_stats(const float* logits0, const float* logits1, const float
     return ONDA_OK;
 }
 
-int onda_allreduce_oneshot(float* local, size_t n, int rank, int world, void* const* peer_bufs_host,
+int onda_allreduce_oneshot(float* out, size_t n, int rank, int world, void* const* peer_bufs_host,
                            void* const* peer_flags_host, uint32_t epoch, void* stream) {
-    (void)local; (void)n; (void)rank; (void)world; (void)peer_bufs_host; (void)peer_flags_host; (void)epoch; (void)stream;
-    set_error("onda_allreduce_oneshot: not built yet");
-    return ONDA_EUNSUPPORTED;
+    ONDA_REQUIRE(out && peer_bufs_host && peer_flags_host, "onda_allreduce_oneshot: null pointer");
+    ONDA_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "onda_allreduce_oneshot: bad rank %d / world %d", rank, world);
+    ONDA_REQUIRE(epoch != 0, "onda_allreduce_oneshot: epoch 0 is the flags' initial value");
+    for (int r = 0; r < world; ++r)
+        ONDA_REQUIRE(peer_bufs_host[r] && peer_flags_host[r], "onda_allreduce_oneshot: null peer pointer for rank %d", r);
+    return launch_allreduce_oneshot(out, n, rank, world, peer_bufs_host, peer_flags_host, epoch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

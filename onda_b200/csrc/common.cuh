@@ -46,7 +46,7 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 // Dp = D rounded up to 32; padded channels carry w = 0, Q = 0 so they contribute nothing.
 struct TableLayout {
     int C, D, Dp, CP;
-    size_t off_sigma, off_w, off_mu, off_bias, off_q, off_qhi, off_qlo, total;
+    size_t off_sigma, off_w, off_mu, off_bias, off_q, off_qhi, off_qlo, off_scratch, total;
 };
 __host__ __device__ inline TableLayout table_layout(int C, int D) {
     TableLayout t;
@@ -58,7 +58,8 @@ __host__ __device__ inline TableLayout table_layout(int C, int D) {
     t.off_q = t.off_bias + 32;
     t.off_qhi = t.off_q + (size_t)t.Dp * t.CP;
     t.off_qlo = t.off_qhi + (size_t)32 * t.Dp;
-    t.total = t.off_qlo + (size_t)32 * t.Dp;
+    t.off_scratch = t.off_qlo + (size_t)32 * t.Dp;          // per-CTA bias partials (doubles) + ticket of the table kernel
+    t.total = t.off_scratch + (size_t)2 * 32 * (t.Dp / 32) + 8;
     return t;
 }
 

@@ -24,6 +24,7 @@ import weakref
 import torch
 
 from . import _native as nat
+from . import sharding
 
 
 def _stream_ptr(device):
@@ -36,13 +37,15 @@ class prototype_handler:
     Reference: prototype_handler.py:9-35 for the constructor.  Extra keyword arguments
     (not in the reference): ``impl`` selects the kernel ("auto" | "simt" | "tcgen05"),
     ``process_group`` makes ``ma``/``append`` sum their class statistics over the ranks of a
-    ``torch.distributed`` group so every rank keeps identical prototypes, ``fuse_hard_soft``
+    ``torch.distributed`` group so every rank keeps identical prototypes (``allreduce="nccl"`` uses
+    ``dist.all_reduce``, ``"oneshot"`` the library's own one-launch NVLink peer-memory kernel), ``fuse_hard_soft``
     lets a ``pseudo_labels(soft=True)`` call that directly follows the hard call on the very
     same tensors reuse that launch.
     """
 
     def __init__(self, ma_lambda=0.9999, tau=1, thresh=0, distance_metric="euclidean",
-                 confidence_regularization_threshold=1, impl="auto", process_group=None, fuse_hard_soft=True):
+                 confidence_regularization_threshold=1, impl="auto", process_group=None, fuse_hard_soft=True,
+                 allreduce="nccl"):
         self.prototypes = 0  # classes x features once appended / loaded (prototype_handler.py:17)
         self.squared_mean = 0
         self.counter = 0
@@ -65,6 +68,11 @@ class prototype_handler:
             raise ValueError(f"unknown impl {impl!r}")
         self.impl = impl
         self.process_group = process_group
+        if allreduce not in ("nccl", "oneshot"):
+            raise ValueError(f"unknown allreduce {allreduce!r}")
+        self.allreduce = allreduce     # "nccl": torch.distributed all_reduce; "oneshot": own NVLink peer-memory kernel
+        self._symm = None              # (tensor, handle, n) of the one-shot all-reduce
+        self._ar_calls = 0
         self.fuse_hard_soft = fuse_hard_soft
         self._stats_src = None     # (sums, C, D) of the last fused pass
         self._stats_cache = None
@@ -146,19 +154,23 @@ class prototype_handler:
                 setattr(self, name, t.to(device=device, dtype=torch.float32).contiguous())
         return self.prototypes, self.squared_mean, self.counter
 
+    def _table_key(self, P, S, cnt, need_stats, device):
+        C, D = P.shape
+        return (self._epoch, P.data_ptr(), P._version,
+                S.data_ptr() if need_stats else 0, S._version if need_stats else 0,
+                cnt.data_ptr() if need_stats else 0, cnt._version if need_stats else 0, C, D, str(device))
+
     def _distance_table(self, metric, device):
         need_stats = metric == "mahalanobis"
         P, S, cnt = self._state(device, need_stats)
         C, D = P.shape
         if C > nat.MAX_CLASSES:
             raise ValueError(f"{C} classes unsupported (max {nat.MAX_CLASSES})")
-        key = (self._epoch, P.data_ptr(), P._version,
-               S.data_ptr() if need_stats else 0, S._version if need_stats else 0,
-               cnt.data_ptr() if need_stats else 0, cnt._version if need_stats else 0, C, D, str(device))
+        key = self._table_key(P, S, cnt, need_stats, device)
         hit = self._table.get(metric)
         if hit is not None and hit[0] == key:
             return hit[1]
-        table = self._buf(("table", metric), (self._lib.onda_table_floats(C, D),), torch.float32, device)
+        table = self._buf(("table", metric), (self._lib.onda_table_floats(C, D),), torch.float32, device, zero=True)
         nat.check(self._lib.onda_build_distance_table(
             nat.ptr(P), nat.ptr(S) if need_stats else None, nat.ptr(cnt) if need_stats else None,
             C, D, nat.METRIC[metric], nat.ptr(table), _stream_ptr(device)), "onda_build_distance_table")
@@ -240,16 +252,7 @@ class prototype_handler:
 
     def _stats_from(self, sums, C, D):
         tail = sums[2 * C * D + C:].tolist()   # one small D2H copy (the reference syncs here too)
-        n = tail[nat.STAT_PIXELS]
-        inv = 1.0 / n if n > 0 else float("nan")
-        return {
-            "prototypes": tail[nat.STAT_PROTO_CONF] * inv,
-            "prior": tail[nat.STAT_PRIOR_CONF] * inv,
-            "pseudolabel confidence": tail[nat.STAT_PL_CONF] * inv,
-            "pseudolabel_pixel_num": tail[nat.STAT_PL_PIXELS],
-            "entropy": tail[nat.STAT_ENTROPY] * inv,
-            "pixels": n,
-        }
+        return sharding.stats_from_tail(tail)
 
     @property
     def last_stats(self):
@@ -389,10 +392,39 @@ class prototype_handler:
         return sums, D, C, feat3.device
 
     def _allreduce(self, sums):
-        if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.process_group)
+        if self.process_group is None:
+            return sums
+        if self.allreduce == "oneshot" and sums.is_cuda:
+            return self._allreduce_oneshot(sums)
+        sharding.allreduce_sums(sums, self.process_group)
         return sums
+
+    def _allreduce_oneshot(self, sums):
+        """Sum over the ranks with onda_allreduce_oneshot: inputs in symmetric (peer-mapped) memory, two slots."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        n = sums.numel()
+        world, rank = dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+        slot_floats = (n + 63) // 64 * 64
+        if self._symm is None or self._symm[2] != n:
+            buf = symm_mem.empty(2 * slot_floats + 64, dtype=torch.float32, device=sums.device)
+            hdl = symm_mem.rendezvous(buf, self.process_group)
+            buf.zero_()
+            torch.cuda.synchronize(sums.device)
+            dist.barrier(group=self.process_group)
+            self._symm = (buf, hdl, n)
+            self._ar_calls = 0
+        buf, hdl, _ = self._symm
+        slot = self._ar_calls & 1
+        self._ar_calls += 1
+        buf[slot * slot_floats: slot * slot_floats + n].copy_(sums)      # rank-local staging into the peer-visible slot
+        ptr_t = nat.C.c_void_p * world
+        bufs = ptr_t(*[int(p) + 4 * slot * slot_floats for p in hdl.buffer_ptrs])
+        flags = ptr_t(*[int(p) + 4 * (2 * slot_floats + 32 * slot) for p in hdl.buffer_ptrs])
+        out = torch.empty_like(sums)
+        nat.check(self._lib.onda_allreduce_oneshot(nat.ptr(out), n, rank, world, bufs, flags, self._ar_calls,
+                                                   _stream_ptr(sums.device)), "onda_allreduce_oneshot")
+        return out
 
     def get_proto_array(self, feat, out):
         """(class sums (C, D), pixel counts (C,)) keyed by argmax of ``out`` (:76-81)."""
@@ -413,9 +445,21 @@ class prototype_handler:
             raise AttributeError("squared_mean is not initialised")
         if P.shape != (C, D):
             raise ValueError(f"feat/out give a {C}x{D} update but prototypes are {tuple(P.shape)}")
-        nat.check(self._lib.onda_ema_update(nat.ptr(P), nat.ptr(S), nat.ptr(sums), C, D, float(self.ma_lambda),
-                                            _stream_ptr(device)), "onda_ema_update")
+        metric = self.distance_metric
+        need_stats = metric == "mahalanobis"
+        cnt = self.counter if isinstance(self.counter, torch.Tensor) else None
+        if need_stats and cnt is None:
+            nat.check(self._lib.onda_ema_update(nat.ptr(P), nat.ptr(S), nat.ptr(sums), C, D, float(self.ma_lambda),
+                                                _stream_ptr(device)), "onda_ema_update")
+            self._epoch += 1
+            return
+        # blend and rebuild the distance table for the next step in one launch
+        table = self._buf(("table", metric), (self._lib.onda_table_floats(C, D),), torch.float32, device, zero=True)
+        nat.check(self._lib.onda_ema_update_and_table(
+            nat.ptr(P), nat.ptr(S), nat.ptr(cnt) if need_stats else None, nat.ptr(sums), C, D, float(self.ma_lambda),
+            nat.METRIC[metric], nat.ptr(table), _stream_ptr(device)), "onda_ema_update_and_table")
         self._epoch += 1
+        self._table = {metric: (self._table_key(P, S, cnt, need_stats, device), table)}
 
     def append(self, feat, out):
         """Cumulative-mean update used to initialise the prototypes (:62-74)."""
