@@ -71,7 +71,7 @@ class prototype_handler:
         if allreduce not in ("nccl", "oneshot"):
             raise ValueError(f"unknown allreduce {allreduce!r}")
         self.allreduce = allreduce     # "nccl": torch.distributed all_reduce; "oneshot": own NVLink peer-memory kernel
-        self._symm = None              # (tensor, handle, n) of the one-shot all-reduce
+        self._symm = None              # (tensor, handle, n, slot_floats) of the one-shot all-reduce
         self._ar_calls = 0
         self.fuse_hard_soft = fuse_hard_soft
         self._stats_src = None     # (sums, C, D) of the last fused pass
@@ -187,7 +187,11 @@ class prototype_handler:
         labels = torch.empty((N, 1), dtype=torch.int64, device=device) if want_labels else None
         soft = torch.empty((N, C), dtype=torch.float32, device=device) if want_soft else None
         dist = torch.empty((N, C), dtype=torch.float32, device=device) if want_dist else None
-        sums = torch.empty((self._lib.onda_sums_floats(C, D),), dtype=torch.float32, device=device)
+        n_sums = self._lib.onda_sums_floats(C, D)
+        if self.process_group is not None and self.allreduce == "oneshot" and logits3 is not None:
+            sums = self._symm_slot(n_sums, device)      # written straight into peer-visible memory: no staging copy
+        else:
+            sums = torch.empty((n_sums,), dtype=torch.float32, device=device)
         impl = nat.IMPL[self.impl]
         wbytes = self._lib.onda_fused_workspace_bytes(B, D, HW, C, impl)
         work = self._buf("work", (wbytes,), torch.uint8, device)
@@ -399,29 +403,41 @@ class prototype_handler:
         sharding.allreduce_sums(sums, self.process_group)
         return sums
 
+    def _symm_init(self, n, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        slot_floats = (n + 63) // 64 * 64
+        buf = symm_mem.empty(2 * slot_floats + 64, dtype=torch.float32, device=device)
+        hdl = symm_mem.rendezvous(buf, self.process_group)
+        buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.process_group)
+        self._symm = (buf, hdl, n, slot_floats)
+        self._ar_calls = 0
+
+    def _symm_slot(self, n, device):
+        """The peer-visible input slot of the next one-shot all-reduce (two slots, alternating per call)."""
+        if self._symm is None or self._symm[2] != n:
+            self._symm_init(n, device)
+        buf, _, _, slot_floats = self._symm
+        slot = self._ar_calls & 1
+        return buf[slot * slot_floats: slot * slot_floats + n]
+
     def _allreduce_oneshot(self, sums):
         """Sum over the ranks with onda_allreduce_oneshot: inputs in symmetric (peer-mapped) memory, two slots."""
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
         n = sums.numel()
         world, rank = dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
-        slot_floats = (n + 63) // 64 * 64
-        if self._symm is None or self._symm[2] != n:
-            buf = symm_mem.empty(2 * slot_floats + 64, dtype=torch.float32, device=sums.device)
-            hdl = symm_mem.rendezvous(buf, self.process_group)
-            buf.zero_()
-            torch.cuda.synchronize(sums.device)
-            dist.barrier(group=self.process_group)
-            self._symm = (buf, hdl, n)
-            self._ar_calls = 0
-        buf, hdl, _ = self._symm
+        slot_view = self._symm_slot(n, sums.device)
+        buf, hdl, _, slot_floats = self._symm
         slot = self._ar_calls & 1
+        if sums.data_ptr() != slot_view.data_ptr():
+            slot_view.copy_(sums)                       # input was produced elsewhere: stage it
         self._ar_calls += 1
-        buf[slot * slot_floats: slot * slot_floats + n].copy_(sums)      # rank-local staging into the peer-visible slot
         ptr_t = nat.C.c_void_p * world
         bufs = ptr_t(*[int(p) + 4 * slot * slot_floats for p in hdl.buffer_ptrs])
         flags = ptr_t(*[int(p) + 4 * (2 * slot_floats + 32 * slot) for p in hdl.buffer_ptrs])
-        out = torch.empty_like(sums)
+        out = torch.empty((n,), dtype=torch.float32, device=sums.device)
         nat.check(self._lib.onda_allreduce_oneshot(nat.ptr(out), n, rank, world, bufs, flags, self._ar_calls,
                                                    _stream_ptr(sums.device)), "onda_allreduce_oneshot")
         return out
@@ -436,8 +452,9 @@ class prototype_handler:
         self._deferred_monitor = None
         sums, D, C, device = self._class_sums(feat, out)
         sums = self._allreduce(sums)
-        if self._deferred_monitor is not None:   # global statistics are available only now
+        if self.process_group is not None:       # the statistics tail is global (all ranks) only now
             self._stats_src, self._stats_cache = (sums, C, D), None
+        if self._deferred_monitor is not None:
             self._monitor_side_effects(self._deferred_monitor, self.last_stats)
             self._deferred_monitor = None
         P, S, _ = self._state(device, False)
