@@ -276,12 +276,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             unsigned n = tile * kTilePixels + 32 * quarter + lane;
             n = n < Nu ? n : Nu - 1;         // clamp: results of padded rows are never stored (epilogue / sorter guard them)
             const unsigned bimg = n / HWu, pix = n - bimg * HWu;
-            const char* src = reinterpret_cast<const char*>(p.feat + ((size_t)bimg * D + (size_t)b * kTcChunkC) * HWu + pix);
-            const size_t plane = (size_t)HWu * sizeof(float);       // one 64-bit add per load, no multiplies
+            unsigned long long src = reinterpret_cast<unsigned long long>(p.feat + ((size_t)bimg * D + (size_t)b * kTcChunkC) * HWu + pix);
+            const unsigned long long plane = (unsigned long long)HWu * sizeof(float);
 #pragma unroll
-            for (int j = 0; j < kTcChunkC; ++j) {
-                x[j] = ldg_stream(reinterpret_cast<const float*>(src));
-                src += plane;
+            for (int j = 0; j < kTcChunkC; ++j) {   // one dependent 64-bit add per load (kept as a chain: no table of 32 offsets)
+                asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];\n\tadd.s64 %1, %1, %2;"
+                             : "=f"(x[j]), "+l"(src) : "l"(plane));
             }
         };
         if (group < total_chunks) issue_loads(group);
@@ -354,21 +354,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                         float xv[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const uint32_t ad = tg_lane + (uint32_t)__shfl_sync(0xffffffffu, myoff, e0 + e);   // dead lanes: row 0, unused
+                            const uint32_t ad = tg_lane + (uint32_t)__shfl_sync(0xffffffffu, myoff, e0 + e);   // dead lanes: row 0
                             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[e]) : "r"(ad));
                         }
+                        // entries past the range's end need no guard: the last live entry is a class end, so whatever
+                        // they add to the running pair is never flushed
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            if (e0 + e < nlive) {
-                                s1 += xv[e];
-                                s2 = fmaf(xv[e], xv[e], s2);
-                                if ((endbits >> (e0 + e)) & 1u) {
-                                    const int k = __shfl_sync(0xffffffffu, mycls, e0 + e);
-                                    a1[(size_t)k * D] += s1;
-                                    a2[(size_t)k * D] += s2;
-                                    s1 = 0.f;
-                                    s2 = 0.f;
-                                }
+                            s1 += xv[e];
+                            s2 = fmaf(xv[e], xv[e], s2);
+                            if (endbits & (1u << (e0 + e))) {
+                                const int k = __shfl_sync(0xffffffffu, mycls, e0 + e);
+                                a1[(size_t)k * D] += s1;
+                                a2[(size_t)k * D] += s2;
+                                s1 = 0.f;
+                                s2 = 0.f;
                             }
                         }
                     }
