@@ -60,59 +60,68 @@ static int cached_sm_count() {
 }
 
 // ---- distance table (optionally fused with the EMA blend) ---------------------------------------
-// One warp-sized CTA per 32 channels, thread = channel: every quantity of the table is per channel except the
-// per-class bias, whose per-CTA partial sums are folded by the last CTA to finish, in CTA order (deterministic).
+// One 128-thread CTA per 32 channels: lane = channel, warp g handles the classes k = g, g+4, g+8, ... of that
+// channel (four short dependent chains instead of one long one); per-channel partial moments meet in shared
+// memory and are added in warp order.  Every quantity of the table is per channel except the per-class bias,
+// whose per-CTA partial sums are folded by the last CTA to finish, in CTA order (deterministic).
 // With `sums` != null the moving-average blend of ma() (prototype_handler.py:88-99) is applied to P and S first,
-// in the same thread that then rebuilds the channel's table entries.
-constexpr int kTableThreads = 32;
+// by the same thread that then rebuilds the table entries of that (class, channel).
+constexpr int kTableThreads = 128;
 
 __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict__ P, float* __restrict__ S,
                                                               const float* __restrict__ cnt, int C, int D, int metric,
                                                               float* __restrict__ table, const float* __restrict__ sums,
                                                               float lam) {
     const TableLayout T = table_layout(C, D);
-    const int lane = threadIdx.x;
-    const int j = blockIdx.x * kTableThreads + lane;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
     const bool mahal = metric == ONDA_METRIC_MAHALANOBIS;
     __shared__ double wk[32];              // c_k / sum_k c_k
-    {
+    __shared__ double mom[4][3][32];       // per warp: partial (gm, gsq, mean) of each channel
+    __shared__ double bpart[4][32];        // per warp: partial bias of its classes
+    if (g == 0) {
         double ck = (mahal && lane < C) ? (double)cnt[lane] : 0.0, total = ck;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
         wk[lane] = ck / total;
     }
-    __syncwarp();
-    double b[32];
+    __syncthreads();
+    float pk[8];                            // this thread's classes g, g+4, ... (at most 8 of 32)
+    double gm = 0.0, gsq = 0.0, mean = 0.0;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) b[k] = 0.0;
-    float pk[32];
-    float sigma = 0.f, wf = 0.f, muf = 0.f;
-    if (j < D) {
-        double gm = 0.0, gsq = 0.0, mean = 0.0;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            pk[k] = 0.f;
-            if (k < C) {
-                float pv = P[(size_t)k * D + j];
-                float sv = (mahal || sums != nullptr) ? S[(size_t)k * D + j] : 0.f;
-                if (sums != nullptr) {     // ma(): P <- P*rho + (1-rho)*sum/max(cnt,1), rho = lambda if cnt > 0 else 1
-                    const float n = sums[(size_t)2 * C * D + k];
-                    const float rho = n > 0.f ? lam : 1.f;
-                    const float one_m = __fsub_rn(1.f, rho);
-                    const float den = n > 0.f ? n : 1.f;
-                    pv = __fadd_rn(__fmul_rn(pv, rho), __fmul_rn(one_m, __fdiv_rn(sums[(size_t)k * D + j], den)));
-                    sv = __fadd_rn(__fmul_rn(sv, rho), __fmul_rn(one_m, __fdiv_rn(sums[(size_t)(C + k) * D + j], den)));
-                    P[(size_t)k * D + j] = pv;
-                    S[(size_t)k * D + j] = sv;
-                }
-                pk[k] = pv;
-                mean += (double)pv;
-                if (mahal) {
-                    gm += (double)pv * wk[k];          // global_var(): prototype_handler.py:57-59
-                    gsq += (double)sv * wk[k];         // :54-56
-                }
+    for (int i = 0; i < 8; ++i) {
+        const int k = g + 4 * i;
+        pk[i] = 0.f;
+        if (j < D && k < C) {
+            float pv = P[(size_t)k * D + j];
+            float sv = (mahal || sums != nullptr) ? S[(size_t)k * D + j] : 0.f;
+            if (sums != nullptr) {     // ma(): P <- P*rho + (1-rho)*sum/max(cnt,1), rho = lambda if cnt > 0 else 1
+                const float n = sums[(size_t)2 * C * D + k];
+                const float rho = n > 0.f ? lam : 1.f;
+                const float one_m = __fsub_rn(1.f, rho);
+                const float den = n > 0.f ? n : 1.f;
+                pv = __fadd_rn(__fmul_rn(pv, rho), __fmul_rn(one_m, __fdiv_rn(sums[(size_t)k * D + j], den)));
+                sv = __fadd_rn(__fmul_rn(sv, rho), __fmul_rn(one_m, __fdiv_rn(sums[(size_t)(C + k) * D + j], den)));
+                P[(size_t)k * D + j] = pv;
+                S[(size_t)k * D + j] = sv;
+            }
+            pk[i] = pv;
+            mean += (double)pv;
+            if (mahal) {
+                gm += (double)pv * wk[k];          // global_var(): prototype_handler.py:57-59
+                gsq += (double)sv * wk[k];         // :54-56
             }
         }
+    }
+    mom[g][0][lane] = gm;
+    mom[g][1][lane] = gsq;
+    mom[g][2][lane] = mean;
+    __syncthreads();
+    gm = (mom[0][0][lane] + mom[1][0][lane]) + (mom[2][0][lane] + mom[3][0][lane]);
+    gsq = (mom[0][1][lane] + mom[1][1][lane]) + (mom[2][1][lane] + mom[3][1][lane]);
+    mean = (mom[0][2][lane] + mom[1][2][lane]) + (mom[2][2][lane] + mom[3][2][lane]);
+    float sigma = 0.f, wf = 0.f, muf = 0.f;
+    if (j < D) {
         if (mahal) {
             sigma = (float)sqrt(gsq - gm * gm);        // :60
             wf = (float)(1.0 / ((double)sigma * (double)sigma));
@@ -123,18 +132,23 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
             muf = (float)(mean / C);
         }
     }
-    if (j < T.Dp) {
+    if (g == 0 && j < T.Dp) {
         table[T.off_sigma + j] = sigma;
         table[T.off_w + j] = wf;
         table[T.off_mu + j] = muf;
+    }
+    // table entries and bias of this thread's classes
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            float qf = 0.f;
-            if (j < D && k < C) {
-                const double diff = (double)pk[k] - (double)muf;
-                qf = (float)((double)wf * diff);
-                b[k] += (double)wf * diff * diff;
-            }
+    for (int i = 0; i < 8; ++i) {
+        const int k = g + 4 * i;
+        float qf = 0.f;
+        double bk = 0.0;
+        if (j < D && k < C) {
+            const double diff = (double)pk[i] - (double)muf;
+            qf = (float)((double)wf * diff);
+            bk = (double)wf * diff * diff;
+        }
+        if (j < T.Dp) {
             if (k < T.CP) table[T.off_q + (size_t)j * T.CP + k] = qf;
             // TF32 split of -2*Q in the tcgen05 B-operand layout (common.cuh); classes >= C are zero rows
             const float v = -2.f * qf;
@@ -143,28 +157,26 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
             table[T.off_qhi + bi] = hi;
             table[T.off_qlo + bi] = v - hi;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bk += __shfl_xor_sync(0xffffffffu, bk, o);   // over the CTA's 32 channels
+        if (lane == 0) bpart[g][i] = bk;
     }
-    // per-class bias: warp sum of this CTA's channels, then the last CTA folds all CTAs in order
+    __syncthreads();
+    // per-class bias: this CTA's partial, then the last CTA folds all CTAs in order
     double* part = reinterpret_cast<double*>(table + T.off_scratch);
     unsigned* ticket = reinterpret_cast<unsigned*>(table + T.off_scratch + (size_t)2 * 32 * gridDim.x);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        double v = b[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == k) part[(size_t)blockIdx.x * 32 + k] = v;
-    }
+    __shared__ unsigned last_flag;
+    if (threadIdx.x < 32) part[(size_t)blockIdx.x * 32 + threadIdx.x] = bpart[threadIdx.x & 3][threadIdx.x >> 2];   // class k = g + 4i
     __threadfence();
-    __syncwarp();
-    unsigned last = 0;
-    if (lane == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
+    __syncthreads();
+    if (threadIdx.x == 0) last_flag = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (last_flag && threadIdx.x < 32) {
         __threadfence();
         double v = 0.0;
-        for (unsigned c = 0; c < gridDim.x; ++c) v += __ldcg(part + (size_t)c * 32 + lane);
-        table[T.off_bias + lane] = (float)v;
-        if (lane == 0) *ticket = 0u;        // re-arm for the next build
+        for (unsigned c = 0; c < gridDim.x; ++c) v += __ldcg(part + (size_t)c * 32 + threadIdx.x);
+        table[T.off_bias + threadIdx.x] = (float)v;
+        if (threadIdx.x == 0) *ticket = 0u;        // re-arm for the next build
     }
 }
 

@@ -172,7 +172,7 @@ __device__ __forceinline__ void warp_copy_rows(const float* stage_rows, float* g
 // Tail for one tile row handled by thread `t` (pixel n = tile_base + t).  `stage` is a
 // [128][CP+1] shared-memory slab; rows 32*warp .. 32*warp+31 belong to this warp.
 template <int CP, bool WANT_DIST>
-__device__ __forceinline__ void finish_pixel(const FusedParams& p, float (&d2)[CP], long long tile_base, int t,
+__device__ __forceinline__ void finish_pixel(const FusedParams& p, const int C, float (&d2)[CP], long long tile_base, int t,
                                              float* stage, PixelStats& st, const float* preloaded_prior = nullptr) {
     const int lane = t & 31, warp = t >> 5;
     const long long n = tile_base + t;
@@ -185,14 +185,14 @@ __device__ __forceinline__ void finish_pixel(const FusedParams& p, float (&d2)[C
 #pragma unroll
         for (int k = 0; k < CP; ++k) pri[k] = preloaded_prior[k];
     } else if (valid && have_prior && want_post) {
-        load_pixel_row<CP>(p.prior, p.C, p.HW, n, pri);
+        load_pixel_row<CP>(p.prior, C, p.HW, n, pri);
     } else {
 #pragma unroll
         for (int k = 0; k < CP; ++k) pri[k] = 0.f;
     }
     int label = 0;
     float m = 0.f, maxq = 0.f, maxprior = 0.f, ent = 0.f;
-    rectify_pixel<CP, WANT_DIST>(d2, pri, p.C, p.inv_tau, p.thresh, have_prior && want_post, dsh, label, m, maxq,
+    rectify_pixel<CP, WANT_DIST>(d2, pri, C, p.inv_tau, p.thresh, have_prior && want_post, dsh, label, m, maxq,
                                  maxprior, ent);
     if (valid) {
         st.proto_conf += maxq;
@@ -213,17 +213,17 @@ __device__ __forceinline__ void finish_pixel(const FusedParams& p, float (&d2)[C
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CP; ++k)
-            if (k < p.C) stage[t * (CP + 1) + k] = d2[k];
+            if (k < C) stage[t * (CP + 1) + k] = d2[k];
         __syncwarp();
-        warp_copy_rows<CP>(my_rows, p.soft + warp_base * p.C, rows, p.C, lane);
+        warp_copy_rows<CP>(my_rows, p.soft + warp_base * C, rows, C, lane);
     }
     if (WANT_DIST && p.dist != nullptr) {
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CP; ++k)
-            if (k < p.C) stage[t * (CP + 1) + k] = dsh[k];
+            if (k < C) stage[t * (CP + 1) + k] = dsh[k];
         __syncwarp();
-        warp_copy_rows<CP>(my_rows, p.dist + warp_base * p.C, rows, p.C, lane);
+        warp_copy_rows<CP>(my_rows, p.dist + warp_base * C, rows, C, lane);
     }
 }
 

@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(kSimtThreads, 2) fused_simt_kernel(const Fused
                 const float* bias = p.table + T.off_bias;
 #pragma unroll
                 for (int k = 0; k < CP; ++k) d2[k] = fmaf(-2.f, d2[k], a_tot + __ldg(bias + k));
-                if (p.dist != nullptr) finish_pixel<CP, true>(p, d2, tile_base, tid, dots, st);
-                else finish_pixel<CP, false>(p, d2, tile_base, tid, dots, st);
+                if (p.dist != nullptr) finish_pixel<CP, true>(p, p.C, d2, tile_base, tid, dots, st);
+                else finish_pixel<CP, false>(p, p.C, d2, tile_base, tid, dots, st);
             } else {
                 const long long n = tile_base + tid;
                 if (n < p.N) {
@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(kSimtThreads) split_finish_kernel(const FusedP
 #pragma unroll
         for (int k = 0; k < CP; ++k) d2[k] = fmaf(-2.f, d2[k], a_tot + __ldg(bias + k));
         __syncthreads();
-        if (p.dist != nullptr) finish_pixel<CP, true>(p, d2, tile_base, tid, stage, st);
-        else finish_pixel<CP, false>(p, d2, tile_base, tid, stage, st);
+        if (p.dist != nullptr) finish_pixel<CP, true>(p, p.C, d2, tile_base, tid, stage, st);
+        else finish_pixel<CP, false>(p, p.C, d2, tile_base, tid, stage, st);
     }
     __syncthreads();
     write_stat_partial(st, red, p.stat_partials + (size_t)blockIdx.x * kStatSlots, kSimtThreads / 32);

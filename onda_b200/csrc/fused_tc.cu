@@ -64,7 +64,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // Wait with a fixed sleep between probes.  Polling costs issue slots and shared-memory pipeline slots that the
 // working warps need, so roles that wait for long events (epilogue, sorter) pass a long sleep.
-template <int kSleepNs = 64>
+template <int kSleepNs = 200>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
     uint32_t tries = 0;
@@ -74,7 +74,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 // wait that adds its duration to a diagnostic counter when profiling is on
-template <int kSleepNs = 64>
+template <int kSleepNs = 200>
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, long long& acc_cycles) {
     if (!prof) { mbar_wait<kSleepNs>(bar, parity); return; }
     const long long t0 = clock64();
@@ -187,11 +187,12 @@ __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     return s;
 }
 
-template <int CP, bool SUMS, bool WANT_DIST, bool PROF>
+template <int CP, int CE, bool SUMS, bool WANT_DIST, bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int C = p.C, D = p.D, HW = p.HW;
+    const int C = CE > 0 ? CE : p.C;      // CE: class count known at compile time (19 in every OnDA config) -> no k < C predication
+    const int D = p.D, HW = p.HW;
     const int NB = D / kTcChunkC;
     const int nb_shift = NB == 8 ? 3 : 2;              // D = 256 or 128 (tc_supported)
     const TcSmem L = tc_smem(D, C, CP, SUMS);
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                     const int q = t * NB + b;
                     const int stage = q & 3;
                     const uint32_t use = (uint32_t)q >> 2;
-                    mbar_wait_t(full_a(stage), use & 1, prof, dbg[1]);
+                    mbar_wait_t<32>(full_a(stage), use & 1, prof, dbg[1]);
                     tc_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                     for (int k = 0; k < CP; ++k) pri[k] = 0.f;
                 }
             }
-            mbar_wait_t<400>(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
+            mbar_wait_t<800>(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
             tc_fence_after();
             uint32_t dv[32];
             tc_ld32(tmem_base + lane_base + kAccCol0 + (uint32_t)par * 32, dv);
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             float d2[CP];
 #pragma unroll
             for (int k = 0; k < CP; ++k) d2[k] = (a_tot + __ldg(bias + k)) + __uint_as_float(dv[k]);
-            finish_pixel<CP, WANT_DIST>(p, d2, tile * kTilePixels, et, out_stage, st, pri);
+            finish_pixel<CP, WANT_DIST>(p, C, d2, tile * kTilePixels, et, out_stage, st, pri);
         }
         // fixed-order reduction of the statistics over the four epilogue warps
         {
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
 #pragma unroll
             for (int c = 1; c < 4; ++c)
                 cut[c] = (int)__reduce_min_sync(0xffffffffu, (unsigned)((has && cstart >= 32 * c) ? cstart : n_valid));
-            if (t >= 2) mbar_wait_t<400>(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // workers are done with tile t-2
+            if (t >= 2) mbar_wait_t<800>(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // workers are done with tile t-2
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int v = 2 * sw + r;
@@ -566,9 +567,9 @@ bool tc_supported(int B, int D, int HW, int C) {
 
 int tc_grid(int tiles, int sms) { return tiles < sms ? tiles : sms; }
 
-template <int CP, bool SUMS, bool WANT_DIST, bool PROF>
+template <int CP, int CE, bool SUMS, bool WANT_DIST, bool PROF>
 static int launch_tc(const FusedParams& p, int grid, cudaStream_t stream) {
-    auto kern = fused_tc_kernel<CP, SUMS, WANT_DIST, PROF>;
+    auto kern = fused_tc_kernel<CP, CE, SUMS, WANT_DIST, PROF>;
     const size_t smem = tc_smem(p.D, p.C, CP, SUMS).total;
     ONDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     timing_begin(stream);
@@ -579,16 +580,17 @@ static int launch_tc(const FusedParams& p, int grid, cudaStream_t stream) {
     return ONDA_OK;
 }
 
-template <int CP>
+template <int CP, int CE>
 static int launch_tc_cp(const FusedParams& p, int grid, bool sums, cudaStream_t stream) {
     const bool dist = p.dist != nullptr;
-    if (p.debug != nullptr && sums && !dist) return launch_tc<CP, true, false, true>(p, grid, stream);   // diagnostics build
-    if (sums) return dist ? launch_tc<CP, true, true, false>(p, grid, stream) : launch_tc<CP, true, false, false>(p, grid, stream);
-    return dist ? launch_tc<CP, false, true, false>(p, grid, stream) : launch_tc<CP, false, false, false>(p, grid, stream);
+    if (p.debug != nullptr && sums && !dist) return launch_tc<CP, CE, true, false, true>(p, grid, stream);   // diagnostics build
+    if (sums) return dist ? launch_tc<CP, CE, true, true, false>(p, grid, stream) : launch_tc<CP, CE, true, false, false>(p, grid, stream);
+    return dist ? launch_tc<CP, CE, false, true, false>(p, grid, stream) : launch_tc<CP, CE, false, false, false>(p, grid, stream);
 }
 
 int launch_fused_tc(const FusedParams& p, int grid, bool sums, cudaStream_t stream) {
-    return padded_classes(p.C) == 20 ? launch_tc_cp<20>(p, grid, sums, stream) : launch_tc_cp<32>(p, grid, sums, stream);
+    if (p.C == 19) return launch_tc_cp<20, 19>(p, grid, sums, stream);       // the class count of every OnDA config
+    return padded_classes(p.C) == 20 ? launch_tc_cp<20, 0>(p, grid, sums, stream) : launch_tc_cp<32, 0>(p, grid, sums, stream);
 }
 
 }  // namespace onda
