@@ -47,6 +47,18 @@ def algorithmic_bytes_per_pixel(d):
     return 4 * d + 4 * C + 4 * C + 4 * C + 8
 
 
+def measured_traffic(d):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if it does not apply)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_tc_traffic.json")) as f:
+            t = json.load(f)
+        if d == 256:
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -298,7 +310,9 @@ def run_onda(args):
                 "steps": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": f"fused pseudo-label pass ({h.impl})", "kernel_ms": kernel_ms,
+                     "traffic": measured_traffic(d) if args.kernel in ("auto", "tcgen05") else None,
+                     "traffic_source": "profiles/r1_tc_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "kernel": f"fused pseudo-label pass ({h.impl})", "kernel_ms": kernel_ms,
                      "launches_timed": int(n_timed.value), "bytes_per_px": algorithmic_bytes_per_pixel(d),
                      "peak_source": peak_src, "step_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
     }
