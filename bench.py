@@ -224,7 +224,7 @@ def run_onda(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    lib.onda_kernel_timing_enable(1)
+    lib.onda_kernel_timing_enable(4)      # CUDA events around every 4th launch of the dominant kernel (small probe effect)
     launches0 = lib.onda_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -338,9 +338,11 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--allreduce", default="oneshot", choices=["nccl", "oneshot"],
                     help="exchange of the class-sum buffer at N>1: NCCL all_reduce or the library's one-shot NVLink kernel")
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU (default 32 = the bench workload)")
     ap.add_argument("--d", type=int, default=256, help="feature width (256 = real ProDA head, 2048 = stress size)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    globals()["B_PER_GPU"] = args.batch
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -66,6 +66,7 @@ unsigned long long onda_launch_count(void);
 /*
  * Per-kernel timing of the dominant kernel (the fused pass) for the roofline report: when enabled,
  * every onda_pseudolabel_fused call brackets its main kernel with CUDA events on the launch stream.
+ * (`enable` = n > 0 brackets every n-th call, to keep the probe effect on the timed region small; 0 = off).
  * onda_kernel_timing_read synchronises those events and returns the summed duration and the count
  * since the last enable/reset.  Off by default; at most 4096 launches are recorded per window.
  */

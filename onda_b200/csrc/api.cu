@@ -28,13 +28,18 @@ void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n
 
 // ---- optional kernel timing (roofline report) ----------------------------------------------
 constexpr int kMaxTimed = 4096;
-static bool g_timing = false;
+static int g_timing = 0;            // 0 = off, n > 0 = bracket every n-th launch of the dominant kernel
+static int g_timing_seen = 0;
+static bool g_timing_open = false;
 static int g_timed = 0;
 static cudaEvent_t g_ev[kMaxTimed][2];
 static int g_ev_made = 0;
 
 void timing_begin(cudaStream_t s) {
-    if (!g_timing || g_timed >= kMaxTimed) return;
+    g_timing_open = false;
+    if (g_timing <= 0 || g_timed >= kMaxTimed) return;
+    if ((g_timing_seen++ % g_timing) != 0) return;
+    g_timing_open = true;
     while (g_ev_made <= g_timed) {
         cudaEventCreate(&g_ev[g_ev_made][0]);
         cudaEventCreate(&g_ev[g_ev_made][1]);
@@ -43,7 +48,8 @@ void timing_begin(cudaStream_t s) {
     cudaEventRecord(g_ev[g_timed][0], s);
 }
 void timing_end(cudaStream_t s) {
-    if (!g_timing || g_timed >= kMaxTimed) return;
+    if (!g_timing_open) return;
+    g_timing_open = false;
     cudaEventRecord(g_ev[g_timed][1], s);
     ++g_timed;
 }
@@ -383,7 +389,8 @@ int onda_debug_set_buffer(void* device_buffer) {
 }
 
 int onda_kernel_timing_enable(int enable) {
-    g_timing = enable != 0;
+    g_timing = enable > 0 ? enable : 0;
+    g_timing_seen = 0;
     g_timed = 0;
     return ONDA_OK;
 }
@@ -494,7 +501,7 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
                  "onda_pseudolabel_fused: the tcgen05 kernel covers D = 128 or 256 and C <= 32 "
                  "(got D=%d C=%d)", D, C);
     // AUTO: tensor-core kernel when the shape allows and there are enough tiles to fill the machine
-    const bool use_tc = tc_ok && (impl == ONDA_IMPL_TCGEN05 || (impl == ONDA_IMPL_AUTO && n_tiles >= 128));
+    const bool use_tc = tc_ok && (impl == ONDA_IMPL_TCGEN05 || (impl == ONDA_IMPL_AUTO && n_tiles >= 32));
     const Workspace ws = fused_workspace(B, D, HW, C);
     ONDA_REQUIRE(workspace_bytes >= ws.total, "onda_pseudolabel_fused: workspace too small (%zu < %zu)", workspace_bytes,
                  ws.total);
