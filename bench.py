@@ -108,7 +108,7 @@ class ClockSampler:
                 "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
 
 
-def gpu_inputs(torch, device, d, n_sets, seed):
+def gpu_inputs(torch, device, d, n_sets, seed, block=8, margin=4.0):
     """Synthetic Cityscapes-shaped inputs generated on the device (SURVEY.md 8d recipe)."""
     g = torch.Generator(device=device).manual_seed(seed)
     protos = torch.randn(C, d, generator=g, device=device) * 2.5
@@ -116,14 +116,15 @@ def gpu_inputs(torch, device, d, n_sets, seed):
     counter = torch.floor(torch.rand(C, generator=g, device=device) * 6.9e4 + 1e3)
     sets = []
     for _ in range(n_sets):
-        lab = torch.randint(0, C, (B_PER_GPU, (H + 7) // 8, (W + 7) // 8), generator=g, device=device)
-        lab = lab.repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :H, :W]
+        lab = torch.randint(0, C, (B_PER_GPU, (H + block - 1) // block, (W + block - 1) // block),
+                            generator=g, device=device)
+        lab = lab.repeat_interleave(block, 1).repeat_interleave(block, 2)[:, :H, :W]
         feat = torch.randn(B_PER_GPU, d, H, W, generator=g, device=device) * 2.5
         feat += 0.5 * protos[lab].permute(0, 3, 1, 2)
         keep = (torch.rand(B_PER_GPU, d, 1, 1, generator=g, device=device) >= 0.1).float() / 0.9
         feat *= keep                                   # Dropout2d pattern of the EMA model in train() mode
         hot = torch.nn.functional.one_hot(lab, C).permute(0, 3, 1, 2).float()
-        out = torch.randn(B_PER_GPU, C, H, W, generator=g, device=device) * 3 + 4 * hot
+        out = torch.randn(B_PER_GPU, C, H, W, generator=g, device=device) * 3 + margin * hot
         prior = (torch.randn(B_PER_GPU, C, H, W, generator=g, device=device) * 3 + 4 * hot).softmax(1)
         sets.append((feat.contiguous(), prior.contiguous(), out.contiguous()))
     return protos, sq_mean, counter, sets
@@ -198,7 +199,7 @@ def run_onda(args):
     N = B_PER_GPU * H * W
     lib = nat.load()
 
-    protos, sq_mean, counter, sets = gpu_inputs(torch, device, d, 2, 1234 + rank)
+    protos, sq_mean, counter, sets = gpu_inputs(torch, device, d, 2, 1234 + rank, block=args.label_block, margin=args.logit_margin)
     if world > 1:   # identical prototypes everywhere
         for t in (protos, sq_mean, counter):
             dist.broadcast(t, 0)
@@ -339,6 +340,8 @@ def main():
     ap.add_argument("--allreduce", default="oneshot", choices=["nccl", "oneshot"],
                     help="exchange of the class-sum buffer at N>1: NCCL all_reduce or the library's one-shot NVLink kernel")
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (default 32 = the bench workload)")
+    ap.add_argument("--label-block", type=int, default=8, help="side of the constant-label blocks of the synthetic maps")
+    ap.add_argument("--logit-margin", type=float, default=4.0, help="logit bonus of the block's label (coherence of the argmax)")
     ap.add_argument("--d", type=int, default=256, help="feature width (256 = real ProDA head, 2048 = stress size)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

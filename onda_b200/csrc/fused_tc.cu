@@ -135,6 +135,10 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16])
         ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
           "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -304,23 +308,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const float4* mu4 = reinterpret_cast<const float4*>(mus + b * kTcChunkC);
             const float4* w4 = reinterpret_cast<const float4*>(wsm + b * kTcChunkC);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t hi[16], lo[16];
+            for (int part = 0; part < 4; ++part) {       // eight channels at a time: bounds the live registers
+                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 m = mu4[half * 4 + j4], wv = w4[half * 4 + j4];
+                for (int j4 = 0; j4 < 2; ++j4) {
+                    const float4 m = mu4[part * 2 + j4], wv = w4[part * 2 + j4];
                     const float mm[4] = {m.x, m.y, m.z, m.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int j = j4 * 4 + e;
-                        const float xc = x[half * 16 + j] - mm[e];
+                        const float xc = x[part * 8 + j] - mm[e];
                         a = fmaf(xc * xc, ww[e], a);
                         hi[j] = (__float_as_uint(xc) + 0x1000u) & 0xffffe000u;      // round to TF32 (10-bit mantissa)
                         lo[j] = __float_as_uint(xc - __uint_as_float(hi[j]));       // exact remainder
                     }
                 }
-                tc_st16(tcol + half * 16, hi);
-                tc_st16(tcol + 32 + half * 16, lo);
+                tc_st8(tcol + part * 8, hi);
+                tc_st8(tcol + 32 + part * 8, lo);
             }
             apart[((size_t)par * NB + b) * kTilePixels + 32 * quarter + lane] = a;
             tc_wait_st();
