@@ -76,6 +76,10 @@ int onda_kernel_timing_read(float* total_ms_host, int* launches_host);
 /* Diagnostics: when a device buffer of gridDim*32*8 int64 is set, the tcgen05 kernel records per-warp cycle
  * counters (time spent in each pipeline wait, total) into it.  NULL (default) disables it. */
 int onda_debug_set_buffer(void* device_buffer);
+/* Measurement tool: runs a kernel that performs only the fused pass's loads of `feat` [B, D, HW] (same tile walk,
+ * `workers` warps per SM in groups of four, `smem_bytes` of dynamic shared memory to set the L1 size) and writes
+ * one float per warp to out[sm_count * 32].  Its bandwidth is what this access pattern can reach at best. */
+int onda_debug_load_probe(const float* feat, int B, int D, int HW, int workers, int smem_bytes, float* out, void* stream);
 
 /* ---- buffer sizing (host, no CUDA calls) ----------------------------------- */
 /* floats in a distance table built by onda_build_distance_table */

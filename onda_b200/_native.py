@@ -27,6 +27,7 @@ _SIGNATURES = {
     "onda_sm_count": (C.c_int, []),
     "onda_launch_count": (C.c_ulonglong, []),
     "onda_debug_set_buffer": (C.c_int, [_p]),
+    "onda_debug_load_probe": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
     "onda_kernel_timing_enable": (C.c_int, [C.c_int]),
     "onda_kernel_timing_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "onda_table_floats": (C.c_size_t, [C.c_int, C.c_int]),

@@ -26,6 +26,7 @@
 //                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory.
 // Every mbarrier has one producer side and one consumer side that visit it phase by phase, in order.
 // Two accumulator buffers of 32 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
+#include <utility>
 #include "epilogue.cuh"
 
 namespace onda {
@@ -106,6 +107,11 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
 __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -150,6 +156,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr) : "memory");
 }
 
+// x[J] = feature at plane J of a pixel: the address is one IMAD.WIDE with an immediate plane index (no table of
+// offsets in registers, no dependent chain), the load bypasses L1 allocation (streamed once)
+template <int J>
+__device__ __forceinline__ float ldg_plane(unsigned long long src, unsigned plane_bytes) {
+    float v;
+    asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, %3, %1;\n\tld.global.nc.L1::no_allocate.f32 %0, [a];\n\t}"
+                 : "=f"(v) : "l"(src), "r"(plane_bytes), "n"(J));
+    return v;
+}
+template <int N, int... Js>
+__device__ __forceinline__ void ldg_planes(float (&x)[N], unsigned long long src, unsigned plane_bytes, std::integer_sequence<int, Js...>) {
+    ((x[Js] = ldg_plane<Js>(src, plane_bytes)), ...);
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_bdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -169,24 +189,30 @@ struct TcSmem {
     size_t bhi, blo, tiles, acc, out, apart, mu, w, eoff, ecls, cuts, wc, cnt, red, bars, tmem_ptr, total;  // byte offsets
 };
 __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
+    // Everything whose size does not depend on D or C comes first: its addresses are compile-time offsets from the
+    // shared-memory base and cost no registers (the workers have none to spare).
+    // The total matters beyond fitting: L1 is what the SM's 256 KB leave after the shared-memory carve-out, the
+    // carve-out is one of a few sizes (.., 164, 196, 228 KB), and the kernel is measurably slower with the 28 KB of L1
+    // that 228 KB leave than with the 60 KB of the 196 KB step (the feature loads straddle 128-byte lines; the
+    // second line is the next quarter's first).  Keep total + 1 KB (system) <= 196 KB.
     TcSmem s;
     size_t o = 0;
-    s.bhi = o; o += (size_t)32 * D * 4;
-    s.blo = o; o += (size_t)32 * D * 4;
-    s.tiles = o; o += sums ? (size_t)kTcGroups * kTilePixels * kTcTRow * 4 : 0;
-    s.acc = o; o += sums ? (size_t)2 * C * D * 4 : 0;
-    s.out = o; o += (size_t)kTilePixels * (CP + 1) * 4;
-    s.apart = o; o += (size_t)2 * (D / kTcChunkC) * kTilePixels * 4;
-    s.mu = o; o += (size_t)D * 4;
-    s.w = o; o += (size_t)D * 4;
+    s.bars = o; o += 256;                              // (2 * kTcGroups + 8) mbarriers
+    s.tmem_ptr = o; o += 128;
     s.eoff = o; o += (size_t)2 * kTilePixels * 4;      // per tile parity: row offset of every class-sorted entry
     s.ecls = o; o += (size_t)2 * kTilePixels * 4;      // ... and its class (-1 = padding pixel)
-    s.cuts = o; o += (size_t)2 * 8 * 4;                // ... and the four class-aligned ranges of the sorted order
-    s.wc = o; o += (size_t)4 * 36 * 4;                 // per-warp class histograms of the sorter
-    s.cnt = o; o += 32 * 4;
+    s.cuts = o; o += 128;                              // ... and the four class-aligned ranges of the sorted order
+    s.wc = o; o += 640;                                // per-warp class histograms of the sorter (4 x 36)
+    s.cnt = o; o += 128;
     s.red = o; o += 4 * kStatSlots * 4;
-    s.bars = o; o += (size_t)(2 * kTcGroups + 8) * 8;
-    s.tmem_ptr = o; o += 16;
+    s.tiles = o; o += sums ? (size_t)kTcGroups * kTilePixels * kTcTRow * 4 : 0;
+    s.out = o; o += (size_t)kTilePixels * (CP + 1) * 4;
+    s.mu = o; o += (size_t)D * 4;
+    s.w = o; o += (size_t)D * 4;
+    s.apart = o; o += (size_t)2 * (D / kTcChunkC) * kTilePixels * 4;
+    s.bhi = o; o += (size_t)32 * D * 4;
+    s.blo = o; o += (size_t)32 * D * 4;
+    s.acc = o; o += sums ? (size_t)2 * C * D * 4 : 0;
     s.total = o;
     return s;
 }
@@ -230,7 +256,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         Blo[i] = p.table[T.off_qlo + i];
     }
     for (int i = tid; i < D; i += kTcThreads) {
-        mus[i] = p.table[T.off_mu + i];
+        mus[i] = -p.table[T.off_mu + i];      // negated: the workers centre with a packed add
         wsm[i] = p.table[T.off_w + i];
     }
     if (SUMS) {
@@ -281,13 +307,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             unsigned n = tile * kTilePixels + 32 * quarter + lane;
             n = n < Nu ? n : Nu - 1;         // clamp: results of padded rows are never stored (epilogue / sorter guard them)
             const unsigned bimg = n / HWu, pix = n - bimg * HWu;
-            unsigned long long src = reinterpret_cast<unsigned long long>(p.feat + ((size_t)bimg * D + (size_t)b * kTcChunkC) * HWu + pix);
-            const unsigned long long plane = (unsigned long long)HWu * sizeof(float);
-#pragma unroll
-            for (int j = 0; j < kTcChunkC; ++j) {   // one dependent 64-bit add per load (kept as a chain: no table of 32 offsets)
-                asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];\n\tadd.s64 %1, %1, %2;"
-                             : "=f"(x[j]), "+l"(src) : "l"(plane));
-            }
+            const unsigned long long src = reinterpret_cast<unsigned long long>(p.feat + ((size_t)bimg * D + (size_t)b * kTcChunkC) * HWu + pix);
+            const unsigned plane = HWu * (unsigned)sizeof(float);
+            ldg_planes(x, src, plane, std::make_integer_sequence<int, kTcChunkC>{});
         };
         if (group < total_chunks) issue_loads(group);
         for (int q = group; q < total_chunks; q += kTcGroups) {
@@ -303,29 +325,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // apart[par] of tile t-2 consumed
             mbar_wait_t(empty_a(group), (use & 1) ^ 1, prof, dbg[2]);
             tc_fence_after();
-            float a = 0.f;
+            uint64_t a2 = 0;                       // sum_j w_j x'_j^2 of the even / odd channels (packed f32x2 math)
             const uint32_t tcol = tmem_base + lane_base + (uint32_t)group * 64;
-            const float4* mu4 = reinterpret_cast<const float4*>(mus + b * kTcChunkC);
-            const float4* w4 = reinterpret_cast<const float4*>(wsm + b * kTcChunkC);
+            const ulonglong2* mu4 = reinterpret_cast<const ulonglong2*>(mus + b * kTcChunkC);     // -mu, two pairs per load
+            const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(wsm + b * kTcChunkC);
+            const uint64_t neg1 = pack2(-1.f, -1.f);
 #pragma unroll
             for (int part = 0; part < 4; ++part) {       // eight channels at a time: bounds the live registers
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int j4 = 0; j4 < 2; ++j4) {
-                    const float4 m = mu4[part * 2 + j4], wv = w4[part * 2 + j4];
-                    const float mm[4] = {m.x, m.y, m.z, m.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+                    const ulonglong2 m = mu4[part * 2 + j4], wv = w4[part * 2 + j4];
+                    const uint64_t mm[2] = {m.x, m.y}, ww[2] = {wv.x, wv.y};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = j4 * 4 + e;
-                        const float xc = x[part * 8 + j] - mm[e];
-                        a = fmaf(xc * xc, ww[e], a);
-                        hi[j] = (__float_as_uint(xc) + 0x1000u) & 0xffffe000u;      // round to TF32 (10-bit mantissa)
-                        lo[j] = __float_as_uint(xc - __uint_as_float(hi[j]));       // exact remainder
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = j4 * 4 + 2 * e;
+                        const uint64_t xc = fadd2(pack2(x[part * 8 + j], x[part * 8 + j + 1]), mm[e]);
+                        a2 = ffma2(fmul2(xc, xc), ww[e], a2);
+                        const uint32_t h0 = ((uint32_t)xc + 0x1000u) & 0xffffe000u;            // round to TF32 (10-bit mantissa)
+                        const uint32_t h1 = ((uint32_t)(xc >> 32) + 0x1000u) & 0xffffe000u;
+                        const uint64_t l2 = ffma2((uint64_t)h0 | ((uint64_t)h1 << 32), neg1, xc);     // exact remainder
+                        hi[j] = h0;
+                        hi[j + 1] = h1;
+                        lo[j] = (uint32_t)l2;
+                        lo[j + 1] = (uint32_t)(l2 >> 32);
                     }
                 }
                 tc_st8(tcol + part * 8, hi);
                 tc_st8(tcol + 32 + part * 8, lo);
             }
+            const float a = __uint_as_float((uint32_t)a2) + __uint_as_float((uint32_t)(a2 >> 32));
             apart[((size_t)par * NB + b) * kTilePixels + 32 * quarter + lane] = a;
             tc_wait_st();
             tc_fence_before();
