@@ -41,6 +41,8 @@ constexpr int kTcChunkC = 32;                    // channels per chunk
 constexpr int kTcTRow = 34;                      // floats per pixel row of a class-sum tile: 32 channels + 2 (conflict-free STS.64 and LDS.32)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = kTcGroups * 64;    // accumulators after the A stages
+constexpr uint32_t kApartCol0 = kAccCol0 + 64;   // then sum_j w_j x'_j^2 of each chunk: 2 tile parities x 8 chunks, lane = pixel
+constexpr int kTcHeadFloats = kTcGroups * 3 * kTcChunkC;   // per statistic: head partials of ranges 1..3 of every group's current chunk
 constexpr uint32_t kSpinLimit = 20000000u;       // failed probes (each followed by a <=256 ns sleep) before giving up
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -145,6 +147,14 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+__device__ __forceinline__ void tc_st1(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -186,7 +196,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------
 struct TcSmem {
-    size_t bhi, blo, tiles, acc, out, apart, mu, w, eoff, ecls, cuts, wc, cnt, red, bars, tmem_ptr, total;  // byte offsets
+    size_t bhi, blo, tiles, acc, out, mu, w, eoff, ecls, cuts, wc, cnt, red, bars, tmem_ptr, total;  // byte offsets
 };
 __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     // Everything whose size does not depend on D or C comes first: its addresses are compile-time offsets from the
@@ -199,9 +209,9 @@ __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     size_t o = 0;
     s.bars = o; o += 256;                              // (2 * kTcGroups + 8) mbarriers
     s.tmem_ptr = o; o += 128;
-    s.eoff = o; o += (size_t)2 * kTilePixels * 4;      // per tile parity: row offset of every class-sorted entry
-    s.ecls = o; o += (size_t)2 * kTilePixels * 4;      // ... and its class (-1 = padding pixel)
-    s.cuts = o; o += 128;                              // ... and the four class-aligned ranges of the sorted order
+    s.eoff = o; o += (size_t)2 * kTilePixels * 4;      // per tile parity: row offset of every class-sorted entry | segment-end flag
+    s.ecls = o; o += (size_t)2 * kTilePixels * 4;      // ... and its accumulator row (class * D; -1 = head segment of its range)
+    s.cuts = o; o += 128;                              // ... [0] live entries, [1..3] the classes cut by the range starts 32, 64, 96
     s.wc = o; o += 640;                                // per-warp class histograms of the sorter (4 x 36)
     s.cnt = o; o += 128;
     s.red = o; o += 4 * kStatSlots * 4;
@@ -209,10 +219,9 @@ __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     s.out = o; o += (size_t)kTilePixels * (CP + 1) * 4;
     s.mu = o; o += (size_t)D * 4;
     s.w = o; o += (size_t)D * 4;
-    s.apart = o; o += (size_t)2 * (D / kTcChunkC) * kTilePixels * 4;
     s.bhi = o; o += (size_t)32 * D * 4;
     s.blo = o; o += (size_t)32 * D * 4;
-    s.acc = o; o += sums ? (size_t)2 * C * D * 4 : 0;
+    s.acc = o; o += sums ? (size_t)2 * (C * D + kTcHeadFloats) * 4 : 0;   // [sum | sum of squares] x [C class rows of D | head partials]
     s.total = o;
     return s;
 }
@@ -231,7 +240,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     float* Tst = reinterpret_cast<float*>(smem_raw + L.tiles);
     float* acc = reinterpret_cast<float*>(smem_raw + L.acc);
     float* out_stage = reinterpret_cast<float*>(smem_raw + L.out);
-    float* apart = reinterpret_cast<float*>(smem_raw + L.apart);
     float* mus = reinterpret_cast<float*>(smem_raw + L.mu);
     float* wsm = reinterpret_cast<float*>(smem_raw + L.w);
     int* eoff = reinterpret_cast<int*>(smem_raw + L.eoff);
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         wsm[i] = p.table[T.off_w + i];
     }
     if (SUMS) {
-        for (int i = tid; i < 2 * C * D; i += kTcThreads) acc[i] = 0.f;
+        for (int i = tid; i < 2 * (C * D + kTcHeadFloats); i += kTcThreads) acc[i] = 0.f;
         if (tid < 32) cnt[tid] = 0;
     }
     if (tid == 0) {
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 for (int j = 0; j < kTcChunkC / 2; ++j) trow[j] = make_float2(x[2 * j], x[2 * j + 1]);
                 named_bar_sync(gbar, 128);          // all 128 pixels of the chunk are staged
             }
-            if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // apart[par] of tile t-2 consumed
+            if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // accumulator and partials [par] of tile t-2 consumed
             mbar_wait_t(empty_a(group), (use & 1) ^ 1, prof, dbg[2]);
             tc_fence_after();
             uint64_t a2 = 0;                       // sum_j w_j x'_j^2 of the even / odd channels (packed f32x2 math)
@@ -355,60 +363,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 tc_st8(tcol + 32 + part * 8, lo);
             }
             const float a = __uint_as_float((uint32_t)a2) + __uint_as_float((uint32_t)(a2 >> 32));
-            apart[((size_t)par * NB + b) * kTilePixels + 32 * quarter + lane] = a;
+            tc_st1(tmem_base + lane_base + kApartCol0 + (uint32_t)(par * 8 + b), __float_as_uint(a));     // read by this pixel's epilogue thread
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(full_a(group));
             if (q + kTcGroups < total_chunks) issue_loads(q + kTcGroups);     // next chunk's loads fly during the class sums
 
             if (SUMS) {
-                // ---- class sums of this chunk's 32 channels (lane = channel) over this warp's quarter of the
-                // class-sorted pixels.  Lane e keeps entry e's row offset and class in registers (broadcast by
-                // shuffle: no dependent shared-memory loads), eight loads are in flight at once, and the class
-                // ends are a warp-uniform bit mask: an end adds the running (sum, sum of squares) to that class.
+                // ---- class sums of this chunk's 32 channels (lane = channel).  The class-sorted pixels of the tile are cut
+                // into four ranges of 32 entries, one per warp of the group: balanced whatever the label map looks like.
+                // Lane e keeps entry e's row offset and the offset of its accumulator row in registers (broadcast by
+                // shuffle: no dependent shared-memory loads), eight loads are in flight at once, and the segment ends
+                // are a warp-uniform bit mask: an end adds the running (sum, sum of squares) to that row.  A range that
+                // starts inside a class accumulates that first segment (its "head") into a spare row -- same code, the
+                // sorter just marks those entries -- which the warp that started the class adds to the class row after
+                // the group's barrier, heads in range order.  One writer per accumulator at a time, fixed order, no
+                // atomics.
                 mbar_wait_t(sort_ready(par), ((uint32_t)t >> 1) & 1, prof, dbg[1]);
                 const long long t_seg0 = prof ? clock64() : 0;
                 const int* eo = eoff + par * kTilePixels;
                 const int* ec = ecls + par * kTilePixels;
-                const int lo_cut = cuts[par * 8 + quarter], hi_cut = cuts[par * 8 + quarter + 1];
+                const int* ct = cuts + par * 8;
+                const int stat_stride = C * D + kTcHeadFloats;
                 float* a1 = acc + b * kTcChunkC + lane;
-                float* a2 = a1 + (size_t)C * D;
+                float* a2 = a1 + stat_stride;
+                const int head_base = C * D + group * 3 * kTcChunkC - b * kTcChunkC;    // head j of this group, relative to a1: + (j-1)*32
+                const int idx = 32 * quarter + lane;                                    // this warp's range: entries 32*quarter .. +31
+                int nlive = ct[0] - 32 * quarter;                                       // ct[0] = live entries of the tile
+                nlive = nlive < 0 ? 0 : (nlive > 32 ? 32 : nlive);
+                const int eo_i = eo[idx], er_i = ec[idx];
+                const unsigned endbits = __ballot_sync(0xffffffffu, eo_i & 1);          // segment ends (sorter: class end or entry 31)
+                const int myoff = eo_i & ~1;
+                const int myrow = er_i < 0 ? head_base + (quarter - 1) * kTcChunkC : er_i;    // accumulator row of this entry's segment
                 float s1 = 0.f, s2 = 0.f;
-                for (int blk = lo_cut; blk < hi_cut; blk += 32) {
-                    const int idx = blk + lane;
-                    const bool live = idx < hi_cut;
-                    const int myoff = live ? eo[idx] : 0;
-                    const int mycls = live ? ec[idx] : -1;
-                    const int nxcls = (live && idx + 1 < hi_cut) ? ec[idx + 1] : -2;
-                    const unsigned endbits = __ballot_sync(0xffffffffu, live && nxcls != mycls);
-                    const int nlive = hi_cut - blk < 32 ? hi_cut - blk : 32;
 #pragma unroll
-                    for (int e0 = 0; e0 < 32; e0 += 8) {
-                        if (e0 >= nlive) break;
-                        float xv[8];
+                for (int e0 = 0; e0 < 32; e0 += 8) {
+                    if (e0 >= nlive) break;
+                    float xv[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const uint32_t ad = tg_lane + (uint32_t)__shfl_sync(0xffffffffu, myoff, e0 + e);   // dead lanes: row 0
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[e]) : "r"(ad));
-                        }
-                        // entries past the range's end need no guard: the last live entry is a class end, so whatever
-                        // they add to the running pair is never flushed
+                    for (int e = 0; e < 8; ++e) {
+                        const uint32_t ad = tg_lane + (uint32_t)__shfl_sync(0xffffffffu, myoff, e0 + e);
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[e]) : "r"(ad));
+                    }
+                    // entries past the last live one need no guard: that one ends a segment, so whatever they add to
+                    // the running pair is never flushed
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            s1 += xv[e];
-                            s2 = fmaf(xv[e], xv[e], s2);
-                            if (endbits & (1u << (e0 + e))) {
-                                const int k = __shfl_sync(0xffffffffu, mycls, e0 + e);
-                                a1[(size_t)k * D] += s1;
-                                a2[(size_t)k * D] += s2;
-                                s1 = 0.f;
-                                s2 = 0.f;
-                            }
+                    for (int e = 0; e < 8; ++e) {
+                        s1 += xv[e];
+                        s2 = fmaf(xv[e], xv[e], s2);
+                        if (endbits & (1u << (e0 + e))) {
+                            const int r = __shfl_sync(0xffffffffu, myrow, e0 + e);
+                            a1[r] += s1;
+                            a2[r] += s2;
+                            s1 = 0.f;
+                            s2 = 0.f;
                         }
                     }
                 }
                 if (prof) dbg[3] += clock64() - t_seg0;
-                named_bar_sync(gbar, 128);          // the group is done reading its tile
+                named_bar_sync(gbar, 128);          // the group is done reading its tile; all heads are complete
+                {   // move the heads of the classes this warp started into their class rows
+                    const int hj = (lane >= 1 && lane < 4) ? ct[lane] : -1;
+                    unsigned m = __ballot_sync(0xffffffffu, hj >= 0 && (hj >> 8) == quarter);
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int k = __shfl_sync(0xffffffffu, hj, j) & 0xff;
+                        const int hrow = head_base + (j - 1) * kTcChunkC;
+                        a1[k * D] += a1[hrow];
+                        a2[k * D] += a2[hrow];
+                        a1[hrow] = 0.f;
+                        a2[hrow] = 0.f;
+                    }
+                }
                 if (q + kTcGroups >= total_chunks || ((q + kTcGroups) >> nb_shift) != t) {   // last chunk of this tile for the group
                     if (lane == 0) mbar_arrive(sort_free(par));
                 }
@@ -470,9 +497,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             tc_fence_after();
             uint32_t dv[32];
             tc_ld32(tmem_base + lane_base + kAccCol0 + (uint32_t)par * 32, dv);
+            uint32_t av[8];
+            tc_ld8(tmem_base + lane_base + kApartCol0 + (uint32_t)par * 8, av);
             tc_wait_ld();
             float a_tot = 0.f;
-            for (int b = 0; b < NB; ++b) a_tot += apart[((size_t)par * NB + b) * kTilePixels + et];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) a_tot += b < NB ? __uint_as_float(av[b]) : 0.f;
             tc_fence_before();
             mbar_arrive(acc_empty(par));
             float d2[CP];
@@ -545,26 +575,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const int n_valid = __shfl_sync(0xffffffffu, incl, 31);
             const int cstart = incl - tot;
             const bool has = tot > 0 && lane < C;
-            // cut c = first class boundary at or after entry 32*c (c = 1..3)
-            int cut[4];
-            cut[0] = 0;
+            // the ranges of the four worker warps start at entries 32, 64, 96: cutcls[c] = the class that runs across
+            // entry 32*c | the worker warp holding that class's first entry << 8, or -1 when a class starts there
+            int cutcls[4];
 #pragma unroll
-            for (int c = 1; c < 4; ++c)
-                cut[c] = (int)__reduce_min_sync(0xffffffffu, (unsigned)((has && cstart >= 32 * c) ? cstart : n_valid));
+            for (int c = 1; c < 4; ++c) {
+                const bool inside = has && cstart < 32 * c && 32 * c < cstart + tot;
+                const unsigned who = __ballot_sync(0xffffffffu, inside);
+                const int val = __shfl_sync(0xffffffffu, lane | ((cstart >> 5) << 8), who ? __ffs(who) - 1 : 0);
+                cutcls[c] = who ? val : -1;
+            }
             if (t >= 2) mbar_wait_t<800>(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // workers are done with tile t-2
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int v = 2 * sw + r;
-                int base = __shfl_sync(0xffffffffu, cstart, bucket[r] & 31);
-                if (bucket[r] == 32) base = n_valid;
+                const int cs = __shfl_sync(0xffffffffu, cstart, bucket[r] & 31);      // first entry and size of this pixel's class
+                const int ct_ = __shfl_sync(0xffffffffu, tot, bucket[r] & 31);
+                int base = bucket[r] == 32 ? n_valid : cs;
                 for (int v2 = 0; v2 < v; ++v2) base += wc[v2 * 36 + bucket[r]];
                 const int pos = base + __popc(peers[r] & lt_mask);
-                eoff[par * kTilePixels + pos] = (32 * v + lane) * (kTcTRow * 4);
-                ecls[par * kTilePixels + pos] = y[r];
+                const bool valid = bucket[r] != 32;
+                const bool seg_end = valid && (pos == cs + ct_ - 1 || (pos & 31) == 31);      // last of its class, or of its range
+                const bool in_head = valid && cs < (pos & ~31);                                // the class began in an earlier range
+                eoff[par * kTilePixels + pos] = ((32 * v + lane) * (kTcTRow * 4)) | (seg_end ? 1 : 0);   // row offset (even) | end flag
+                ecls[par * kTilePixels + pos] = in_head ? -1 : y[r] * D;                       // accumulator row, -1 = the range's head
             }
             if (sw == 0) {
-                if (lane < 4) cuts[par * 8 + lane] = lane == 0 ? 0 : (lane == 1 ? cut[1] : (lane == 2 ? cut[2] : cut[3]));
-                if (lane == 4) cuts[par * 8 + 4] = n_valid;
+                if (lane < 4) cuts[par * 8 + lane] = lane == 0 ? n_valid : (lane == 1 ? cutcls[1] : (lane == 2 ? cutcls[2] : cutcls[3]));
                 if (lane < C) cnt[lane] += tot;                  // pixel counts per class
             }
             mbar_arrive(sort_ready(par));
@@ -582,7 +619,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     __syncthreads();
     if (SUMS) {
         float* out = p.cta_partials + (size_t)blockIdx.x * sums_floats(C, D);
-        for (int i = tid; i < 2 * C * D; i += kTcThreads) out[i] = acc[i];
+        const int cd = C * D;
+        for (int i = tid; i < 2 * cd; i += kTcThreads) out[i] = i < cd ? acc[i] : acc[kTcHeadFloats + i];
         if (tid < C) out[(size_t)2 * C * D + tid] = (float)cnt[tid];
     }
     if (warp == kTcMmaWarp) {
