@@ -180,6 +180,11 @@ __device__ __forceinline__ void ldg_planes(float (&x)[N], unsigned long long src
     ((x[Js] = ldg_plane<Js>(src, plane_bytes)), ...);
 }
 
+template <int J0, int N, int... Js>
+__device__ __forceinline__ void ldg_planes_part(float (&x)[N], unsigned long long src, unsigned plane_bytes, std::integer_sequence<int, Js...>) {
+    ((x[J0 + Js] = ldg_plane<J0 + Js>(src, plane_bytes)), ...);
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_bdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -309,30 +314,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         const uint32_t tg_lane = smem_u32(Tg) + 4u * lane;           // class sums: lane = channel of the chunk
         const int gbar = 3 + group;                                   // named barrier of the group (128 threads)
         float x[kTcChunkC];
-        auto issue_loads = [&](int q) {
+        const unsigned plane = HWu * (unsigned)sizeof(float);
+        auto load_base = [&](int q) {   // address of channel b*32 of this lane's pixel in chunk q
             const int t = q >> nb_shift, b = q & (NB - 1);
             const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
             unsigned n = tile * kTilePixels + 32 * quarter + lane;
             n = n < Nu ? n : Nu - 1;         // clamp: results of padded rows are never stored (epilogue / sorter guard them)
             const unsigned bimg = n / HWu, pix = n - bimg * HWu;
-            const unsigned long long src = reinterpret_cast<unsigned long long>(p.feat + ((size_t)bimg * D + (size_t)b * kTcChunkC) * HWu + pix);
-            const unsigned plane = HWu * (unsigned)sizeof(float);
-            ldg_planes(x, src, plane, std::make_integer_sequence<int, kTcChunkC>{});
+            return reinterpret_cast<unsigned long long>(p.feat + ((size_t)bimg * D + (size_t)b * kTcChunkC) * HWu + pix);
         };
+        auto issue_loads = [&](int q) { ldg_planes(x, load_base(q), plane, std::make_integer_sequence<int, kTcChunkC>{}); };
         if (group < total_chunks) issue_loads(group);
         for (int q = group; q < total_chunks; q += kTcGroups) {
             const int t = q >> nb_shift, b = q & (NB - 1);
             const int par = t & 1;
             const uint32_t use = (uint32_t)q >> 2;
+            const long long t_it0 = prof ? clock64() : 0;
             if (SUMS) {   // raw values into the group's tile, pixel-major, two channels per 8-byte store
                 float2* trow = reinterpret_cast<float2*>(Tg + (size_t)(32 * quarter + lane) * kTcTRow);
 #pragma unroll
                 for (int j = 0; j < kTcChunkC / 2; ++j) trow[j] = make_float2(x[2 * j], x[2 * j + 1]);
                 named_bar_sync(gbar, 128);          // all 128 pixels of the chunk are staged
             }
+            if (prof) dbg[4] += clock64() - t_it0;
             if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // accumulator and partials [par] of tile t-2 consumed
             mbar_wait_t(empty_a(group), (use & 1) ^ 1, prof, dbg[2]);
             tc_fence_after();
+            const long long t_cv0 = prof ? clock64() : 0;
             uint64_t a2 = 0;                       // sum_j w_j x'_j^2 of the even / odd channels (packed f32x2 math)
             const uint32_t tcol = tmem_base + lane_base + (uint32_t)group * 64;
             const ulonglong2* mu4 = reinterpret_cast<const ulonglong2*>(mus + b * kTcChunkC);     // -mu, two pairs per load
@@ -364,10 +372,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             }
             const float a = __uint_as_float((uint32_t)a2) + __uint_as_float((uint32_t)(a2 >> 32));
             tc_st1(tmem_base + lane_base + kApartCol0 + (uint32_t)(par * 8 + b), __float_as_uint(a));     // read by this pixel's epilogue thread
+            const long long t_cv1 = prof ? clock64() : 0;
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(full_a(group));
-            if (q + kTcGroups < total_chunks) issue_loads(q + kTcGroups);     // next chunk's loads fly during the class sums
+            const long long t_cv2 = prof ? clock64() : 0;
+            // The next chunk's loads fly during the class sums.  With class sums they are issued eight at a time between
+            // the batches of the summation: 32 back-to-back loads from every warp of a group fill the SM's miss queue and
+            // the warp would sit blocked at the issue (measured: a quarter of the worker's time).
+            const bool more = q + kTcGroups < total_chunks;
+            const unsigned long long nsrc = more ? load_base(q + kTcGroups) : 0ull;
+            if (!SUMS && more) ldg_planes(x, nsrc, plane, std::make_integer_sequence<int, kTcChunkC>{});
+            if (prof) {
+                dbg[5] += t_cv1 - t_cv0;                 // centring / splitting / tcgen05.st issue
+                dbg[6] += t_cv2 - t_cv1;                 // tcgen05.wait::st + arrive
+                dbg[0] += clock64() - t_cv2;             // issuing the next chunk's loads (acc_empty waits are negligible)
+            }
 
             if (SUMS) {
                 // ---- class sums of this chunk's 32 channels (lane = channel).  The class-sorted pixels of the tile are cut
@@ -398,7 +418,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int e0 = 0; e0 < 32; e0 += 8) {
-                    if (e0 >= nlive) break;
+                    if (more) {
+                        if (e0 == 0) ldg_planes_part<0>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                        if (e0 == 8) ldg_planes_part<8>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                        if (e0 == 16) ldg_planes_part<16>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                        if (e0 == 24) ldg_planes_part<24>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                    }
+                    if (e0 >= nlive) continue;
                     float xv[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {

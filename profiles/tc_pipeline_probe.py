@@ -21,7 +21,7 @@ torch.cuda.synchronize()
 lib.onda_debug_set_buffer(None)
 d = buf.view(148, 32, 8).double().cpu()
 tot = d[:, :, 7]
-names = {"worker": (0, 16, ["wait acc_empty", "wait sort_ready", "wait empty_a(mma)", "class-sum phase"]),
+names = {"worker": (0, 16, ["wait acc_empty + load issue", "wait sort_ready", "wait empty_a(mma)", "class-sum phase", "staging + group barrier 1", "convert + tcgen05.st issue", "tcgen05.wait::st + arrive"]),
          "epilogue": (16, 20, ["wait acc_full"]), "sorter": (20, 24, ["wait sort_free"]),
          "mma": (24, 25, ["wait acc_empty", "wait full_a"])}
 print("mean total cycles per warp:", tot[:, :25].mean().item())
