@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             mbar_wait_t(empty_a(group), (use & 1) ^ 1, prof, dbg[2]);
             tc_fence_after();
             const long long t_cv0 = prof ? clock64() : 0;
+            const bool more = q + kTcGroups < total_chunks;
+            const unsigned long long nsrc = more ? load_base(q + kTcGroups) : 0ull;
             uint64_t a2 = 0;                       // sum_j w_j x'_j^2 of the even / odd channels (packed f32x2 math)
             const uint32_t tcol = tmem_base + lane_base + (uint32_t)group * 64;
             const ulonglong2* mu4 = reinterpret_cast<const ulonglong2*>(mus + b * kTcChunkC);     // -mu, two pairs per load
@@ -369,6 +371,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 }
                 tc_st8(tcol + part * 8, hi);
                 tc_st8(tcol + 32 + part * 8, lo);
+                if (more) {   // the registers of channels 0..15 are free again: their next loads start here
+                    if (part == 1) ldg_planes_part<0>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                    if (part == 3) ldg_planes_part<8>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                }
             }
             const float a = __uint_as_float((uint32_t)a2) + __uint_as_float((uint32_t)(a2 >> 32));
             tc_st1(tmem_base + lane_base + kApartCol0 + (uint32_t)(par * 8 + b), __float_as_uint(a));     // read by this pixel's epilogue thread
@@ -380,9 +386,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             // The next chunk's loads fly during the class sums.  With class sums they are issued eight at a time between
             // the batches of the summation: 32 back-to-back loads from every warp of a group fill the SM's miss queue and
             // the warp would sit blocked at the issue (measured: a quarter of the worker's time).
-            const bool more = q + kTcGroups < total_chunks;
-            const unsigned long long nsrc = more ? load_base(q + kTcGroups) : 0ull;
-            if (!SUMS && more) ldg_planes(x, nsrc, plane, std::make_integer_sequence<int, kTcChunkC>{});
+            if (!SUMS && more) {
+                ldg_planes_part<16>(x, nsrc, plane, std::make_integer_sequence<int, 16>{});
+            }
             if (prof) {
                 dbg[5] += t_cv1 - t_cv0;                 // centring / splitting / tcgen05.st issue
                 dbg[6] += t_cv2 - t_cv1;                 // tcgen05.wait::st + arrive
@@ -419,10 +425,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
 #pragma unroll
                 for (int e0 = 0; e0 < 32; e0 += 8) {
                     if (more) {
-                        if (e0 == 0) ldg_planes_part<0>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
-                        if (e0 == 8) ldg_planes_part<8>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
-                        if (e0 == 16) ldg_planes_part<16>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
-                        if (e0 == 24) ldg_planes_part<24>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                        if (e0 == 0) ldg_planes_part<16>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                        if (e0 == 16) ldg_planes_part<24>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
                     }
                     if (e0 >= nlive) continue;
                     float xv[8];
