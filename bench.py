@@ -231,8 +231,10 @@ def run_onda(args):
     barrier()
     t_wall0 = time.time()
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         step(i)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps      # host time to enqueue one step (no sync inside)
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -304,8 +306,8 @@ def run_onda(args):
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(d, world, args.allreduce),
+        "ms_per_step": ms / args.steps, "host_enqueue_ms_per_step": host_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(d, world, args.allreduce),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps},

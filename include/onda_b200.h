@@ -169,6 +169,17 @@ size_t onda_prior_workspace_bytes(int B, int C, int HW);
 int onda_allreduce_oneshot(float* out, size_t n, int rank, int world, void* const* peer_bufs_host,
                            void* const* peer_flags_host, uint32_t epoch, void* stream);
 
+/* ma() across ranks in one launch: onda_allreduce_oneshot + onda_ema_update_and_table fused.  Every rank's `sums`
+ * (as written by onda_pseudolabel_fused) sits in its peer-mapped slot peer_bufs[rank]; the kernel does the flag
+ * handshake of the one-shot all-reduce, reads the peers' slots over NVLink, adds them in rank order while it blends
+ * (prototype_handler.py:88-99) and rebuilds the distance table, and writes the reduced buffer to sums_out
+ * (onda_sums_floats(C, D) floats: the statistics tail is global afterwards).  Same slot / flag / epoch rules as
+ * onda_allreduce_oneshot. */
+int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, const float* counter, float* sums_out,
+                                        int C, int D, float ma_lambda, int metric, float* table, int rank, int world,
+                                        void* const* peer_bufs_host, void* const* peer_flags_host, uint32_t epoch,
+                                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

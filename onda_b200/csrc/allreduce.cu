@@ -10,65 +10,17 @@
 
 namespace onda {
 
-constexpr int kMaxPeers = 8;
-struct PeerTable {
-    const float* buf[kMaxPeers];      // rank r's input slot, mapped into this process
-    uint32_t* flags[kMaxPeers];       // rank r's flag words for this slot: flags[r][src] = epoch when src is ready
-};
-
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(float* __restrict__ out, size_t n, int rank, int world,
                                                                 PeerTable peers, uint32_t epoch) {
-    // constant-index walks of the pointer tables keep them in the kernel parameter bank (no local-memory copy)
-    uint32_t* flag_of_peer = nullptr;      // for thread r < world: peer r's flag array
-    const uint32_t* my_flags = nullptr;
-#pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r) {
-        if (r == (int)threadIdx.x) flag_of_peer = peers.flags[r];
-        if (r == rank) my_flags = peers.flags[r];
-    }
-    if (blockIdx.x == 0 && threadIdx.x < world) {
-        __threadfence_system();                                   // this rank's input (written by the previous kernel) first
-        st_release_sys(flag_of_peer + rank, epoch);
-    }
-    if (threadIdx.x < world) {
-        const uint32_t* mine = my_flags + threadIdx.x;
-        long long spins = 0;
-        while (ld_acquire_sys(mine) != epoch) {
-            __nanosleep(64);
-            if (++spins > 40000000LL) __trap();                   // a missing peer traps instead of hanging the GPU
-        }
-    }
-    __syncthreads();
+    peer_handshake(peers, rank, world, epoch);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float s = 0.f;
-#pragma unroll
-        for (int r = 0; r < kMaxPeers; ++r)
-            if (r < world) s += ld_relaxed_sys(peers.buf[r] + i);                // fixed order: identical on every rank
-        out[i] = s;
+        out[i] = peer_sum(peers, world, i);
     }
 }
 
 int launch_allreduce_oneshot(float* out, size_t n, int rank, int world, void* const* bufs, void* const* flags,
                              uint32_t epoch, cudaStream_t stream) {
-    PeerTable t;
-    for (int r = 0; r < kMaxPeers; ++r) {
-        t.buf[r] = r < world ? (const float*)bufs[r] : nullptr;
-        t.flags[r] = r < world ? (uint32_t*)flags[r] : nullptr;
-    }
+    const PeerTable t = make_peer_table(rank, world, bufs, flags);
     const int threads = 256;
     int blocks = (int)((n + threads - 1) / threads);
     if (blocks > 64) blocks = 64;

@@ -77,11 +77,65 @@ constexpr int kTableThreads = 128;
 __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict__ P, float* __restrict__ S,
                                                               const float* __restrict__ cnt, int C, int D, int metric,
                                                               float* __restrict__ table, const float* __restrict__ sums,
-                                                              float lam) {
+                                                              float lam, PeerTable peers, int rank, int world,
+                                                              uint32_t epoch, float* __restrict__ sums_out) {
+    // world > 0: `sums` of every rank sit in peer-mapped slots; this kernel is also the all-reduce -- handshake,
+    // then every use of sums[i] is the rank-ordered sum over the peers (identical on every rank), and the reduced
+    // buffer is written to sums_out for the statistics readers.
     const TableLayout T = table_layout(C, D);
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;
     const bool mahal = metric == ONDA_METRIC_MAHALANOBIS;
+    const bool gather = world > 0;
+    __shared__ float cn[32];               // pixel count of every class (the EMA's cnt_k)
+    if (gather) peer_handshake(peers, rank, world, epoch);
+    __shared__ float gs[2 * 32 * 32];      // gather: the reduced (sum | sum of squares)[class][this CTA's 32 channels]
+    if (gather) {
+        // all threads fetch the CTA's slice of every rank's sums with independent (16-byte when possible) loads:
+        // one NVLink round trip per thread instead of one per class
+        const int j0 = blockIdx.x * 32;
+        if (D % 32 == 0) {
+            constexpr int kItems = 2 * ONDA_MAX_CLASSES * 8 / kTableThreads;      // float4 groups per thread (4)
+            size_t gi[kItems];
+            bool on[kItems];
+            float4 v[kItems];
+#pragma unroll
+            for (int it = 0; it < kItems; ++it) {
+                const int item = threadIdx.x + it * kTableThreads;
+                on[it] = item < 2 * C * 8;
+                gi[it] = (size_t)(item >> 3) * D + j0 + (item & 7) * 4;            // row = stat * C + class
+            }
+            if (world <= 2) peer_gather4<2>(peers, world, gi, on, v);
+            else if (world <= 4) peer_gather4<4>(peers, world, gi, on, v);
+            else peer_gather4<8>(peers, world, gi, on, v);
+#pragma unroll
+            for (int it = 0; it < kItems; ++it) {
+                const int item = threadIdx.x + it * kTableThreads;
+                if (on[it]) {
+                    *reinterpret_cast<float4*>(gs + (item >> 3) * 32 + (item & 7) * 4) = v[it];
+                    *reinterpret_cast<float4*>(sums_out + gi[it]) = v[it];
+                }
+            }
+        } else {
+            for (int item = threadIdx.x; item < 2 * C * 32; item += kTableThreads) {
+                const int row = item >> 5, jj = item & 31;
+                if (j0 + jj < D) {
+                    const size_t gi = (size_t)row * D + j0 + jj;
+                    const float v = peer_sum(peers, world, gi);
+                    gs[row * 32 + jj] = v;
+                    sums_out[gi] = v;
+                }
+            }
+        }
+    }
+    if (sums != nullptr || gather) {
+        const size_t tail0 = (size_t)2 * C * D;
+        if ((int)threadIdx.x < C + kStatSlots) {
+            const float v = gather ? peer_sum(peers, world, tail0 + threadIdx.x) : sums[tail0 + threadIdx.x];
+            if ((int)threadIdx.x < C) cn[threadIdx.x] = v;
+            if (gather && blockIdx.x == 0) sums_out[tail0 + threadIdx.x] = v;
+        }
+    }
     __shared__ double wk[32];              // c_k / sum_k c_k
     __shared__ double mom[4][3][32];       // per warp: partial (gm, gsq, mean) of each channel
     __shared__ double bpart[4][32];        // per warp: partial bias of its classes
@@ -100,14 +154,16 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
         pk[i] = 0.f;
         if (j < D && k < C) {
             float pv = P[(size_t)k * D + j];
-            float sv = (mahal || sums != nullptr) ? S[(size_t)k * D + j] : 0.f;
-            if (sums != nullptr) {     // ma(): P <- P*rho + (1-rho)*sum/max(cnt,1), rho = lambda if cnt > 0 else 1
-                const float n = sums[(size_t)2 * C * D + k];
+            float sv = (mahal || sums != nullptr || gather) ? S[(size_t)k * D + j] : 0.f;
+            if (sums != nullptr || gather) {     // ma(): P <- P*rho + (1-rho)*sum/max(cnt,1), rho = lambda if cnt > 0 else 1
+                const float n = cn[k];
                 const float rho = n > 0.f ? lam : 1.f;
                 const float one_m = __fsub_rn(1.f, rho);
                 const float den = n > 0.f ? n : 1.f;
-                pv = __fadd_rn(__fmul_rn(pv, rho), __fmul_rn(one_m, __fdiv_rn(sums[(size_t)k * D + j], den)));
-                sv = __fadd_rn(__fmul_rn(sv, rho), __fmul_rn(one_m, __fdiv_rn(sums[(size_t)(C + k) * D + j], den)));
+                const float sx = gather ? gs[k * 32 + lane] : sums[(size_t)k * D + j];
+                const float sxx = gather ? gs[(C + k) * 32 + lane] : sums[(size_t)(C + k) * D + j];
+                pv = __fadd_rn(__fmul_rn(pv, rho), __fmul_rn(one_m, __fdiv_rn(sx, den)));
+                sv = __fadd_rn(__fmul_rn(sv, rho), __fmul_rn(one_m, __fdiv_rn(sxx, den)));
                 P[(size_t)k * D + j] = pv;
                 S[(size_t)k * D + j] = sv;
             }
@@ -456,7 +512,7 @@ int onda_build_distance_table(const float* prototypes, const float* squared_mean
     if (metric == ONDA_METRIC_MAHALANOBIS)
         ONDA_REQUIRE(squared_mean && counter, "onda_build_distance_table: mahalanobis needs squared_mean and counter");
     table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(const_cast<float*>(prototypes), const_cast<float*>(squared_mean), counter, C, D, metric,
-                                                                                   table, nullptr, 0.f);
+                                                                                   table, nullptr, 0.f, PeerTable{}, 0, 0, 0u, nullptr);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
@@ -561,7 +617,29 @@ int onda_ema_update_and_table(float* prototypes, float* squared_mean, const floa
                  "onda_ema_update_and_table: unexpected value for attribute distance_metric (%d)", metric);
     if (metric == ONDA_METRIC_MAHALANOBIS) ONDA_REQUIRE(counter, "onda_ema_update_and_table: mahalanobis needs counter");
     table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
-                                                                                   table, sums, ma_lambda);
+                                                                                   table, sums, ma_lambda, PeerTable{}, 0, 0, 0u, nullptr);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, const float* counter, float* sums_out,
+                                        int C, int D, float ma_lambda, int metric, float* table, int rank, int world,
+                                        void* const* peer_bufs_host, void* const* peer_flags_host, uint32_t epoch,
+                                        void* stream) {
+    ONDA_REQUIRE(prototypes && squared_mean && sums_out && table && peer_bufs_host && peer_flags_host,
+                 "onda_ema_update_and_table_allreduce: null pointer");
+    ONDA_REQUIRE(C > 0 && C <= ONDA_MAX_CLASSES && D > 0, "onda_ema_update_and_table_allreduce: unsupported shape C=%d D=%d", C, D);
+    ONDA_REQUIRE(metric == ONDA_METRIC_EUCLIDEAN || metric == ONDA_METRIC_MAHALANOBIS,
+                 "onda_ema_update_and_table_allreduce: unexpected value for attribute distance_metric (%d)", metric);
+    if (metric == ONDA_METRIC_MAHALANOBIS) ONDA_REQUIRE(counter, "onda_ema_update_and_table_allreduce: mahalanobis needs counter");
+    ONDA_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "onda_ema_update_and_table_allreduce: bad rank %d / world %d", rank, world);
+    ONDA_REQUIRE(epoch != 0, "onda_ema_update_and_table_allreduce: epoch 0 is the flags' initial value");
+    for (int r = 0; r < world; ++r)
+        ONDA_REQUIRE(peer_bufs_host[r] && peer_flags_host[r], "onda_ema_update_and_table_allreduce: null peer pointer for rank %d", r);
+    const PeerTable peers = make_peer_table(rank, world, peer_bufs_host, peer_flags_host);
+    table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
+                                                                                   table, nullptr, ma_lambda, peers, rank, world, epoch, sums_out);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;

@@ -73,6 +73,93 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
     return v;
 }
 
+// ---- peer memory (one-shot all-reduce over NVLink; allreduce.cu, api.cu) ----------------------------
+constexpr int kMaxPeers = 8;
+struct PeerTable {
+    const float* buf[kMaxPeers];      // rank r's input slot, mapped into this process
+    uint32_t* flags[kMaxPeers];       // rank r's flag words for this slot: flags[r][src] = epoch when src is ready
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+inline PeerTable make_peer_table(int rank, int world, void* const* bufs, void* const* flags) {
+    PeerTable t;
+    for (int r = 0; r < kMaxPeers; ++r) {
+        t.buf[r] = (const float*)bufs[r < world ? r : rank];    // unused entries stay dereferenceable and local (peer_gather4)
+        t.flags[r] = r < world ? (uint32_t*)flags[r] : nullptr;
+    }
+    return t;
+}
+// Handshake of a one-shot exchange: publish "my input is ready" (epoch) on every peer, wait for all peers'.
+// Called by every thread of every CTA; CTA 0 publishes.  Ends with __syncthreads().
+__device__ __forceinline__ void peer_handshake(const PeerTable& peers, int rank, int world, uint32_t epoch) {
+    // constant-index walks of the pointer tables keep them in the kernel parameter bank (no local-memory copy)
+    uint32_t* flag_of_peer = nullptr;      // for thread r < world: peer r's flag array
+    const uint32_t* my_flags = nullptr;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (r == (int)threadIdx.x) flag_of_peer = peers.flags[r];
+        if (r == rank) my_flags = peers.flags[r];
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+        __threadfence_system();                                   // this rank's input (written by the previous kernel) first
+        st_release_sys(flag_of_peer + rank, epoch);
+    }
+    if ((int)threadIdx.x < world) {
+        const uint32_t* mine = my_flags + threadIdx.x;
+        long long spins = 0;
+        while (ld_acquire_sys(mine) != epoch) {
+            __nanosleep(64);
+            if (++spins > 40000000LL) __trap();                   // a missing peer traps instead of hanging the GPU
+        }
+    }
+    __syncthreads();
+}
+// sum over the ranks of element i of the exchanged buffers, in rank order: identical on every rank
+__device__ __forceinline__ float peer_sum(const PeerTable& peers, int world, size_t i) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (r < world) s += ld_relaxed_sys(peers.buf[r] + i);
+    return s;
+}
+
+// Gather of a CTA's slice: element groups of four floats (16-byte aligned) at indices gi[0..ITEMS), summed over the
+// ranks in rank order.  ALL loads (ITEMS x W, W = world rounded up to 1/2/4/8) are issued before the first add, so
+// the slice costs one NVLink round trip.  Entries >= world of the peer table alias this rank's own buffer.
+template <int W, int ITEMS>
+__device__ __forceinline__ void peer_gather4(const PeerTable& peers, int world, const size_t (&gi)[ITEMS], const bool (&on)[ITEMS],
+                                             float4 (&out)[ITEMS]) {
+    float4 v[ITEMS][W];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it)
+#pragma unroll
+        for (int r = 0; r < W; ++r)
+            if (on[it])
+                asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v[it][r].x), "=f"(v[it][r].y), "=f"(v[it][r].z), "=f"(v[it][r].w) : "l"(peers.buf[r] + gi[it]));
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < W; ++r)
+            if (on[it] && r < world) { s.x += v[it][r].x; s.y += v[it][r].y; s.z += v[it][r].z; s.w += v[it][r].w; }
+        out[it] = s;
+    }
+}
+
 // torch.max / argmax semantics: first maximal index, NaN beats everything (first NaN wins).
 __device__ __forceinline__ bool torch_greater(float v, float best) {
     return (v > best) || (v != v && best == best);

@@ -412,33 +412,43 @@ class prototype_handler:
         buf.zero_()
         torch.cuda.synchronize(device)
         dist.barrier(group=self.process_group)
-        self._symm = (buf, hdl, n, slot_floats)
+        world, rank = dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+        ptr_t = nat.C.c_void_p * world
+        peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
+        # per slot: (view of this rank's input, peers' input pointers, peers' flag pointers) -- built once, the step
+        # itself must not spend host time on it
+        slots = []
+        for slot in (0, 1):
+            view = buf[slot * slot_floats: slot * slot_floats + n]
+            bufs = ptr_t(*[p + 4 * slot * slot_floats for p in peer_ptrs])
+            flags = ptr_t(*[p + 4 * (2 * slot_floats + 32 * slot) for p in peer_ptrs])
+            slots.append((view, bufs, flags))
+        self._symm = (buf, hdl, n, slot_floats, slots, rank, world)
         self._ar_calls = 0
 
     def _symm_slot(self, n, device):
         """The peer-visible input slot of the next one-shot all-reduce (two slots, alternating per call)."""
         if self._symm is None or self._symm[2] != n:
             self._symm_init(n, device)
-        buf, _, _, slot_floats = self._symm
-        slot = self._ar_calls & 1
-        return buf[slot * slot_floats: slot * slot_floats + n]
+        return self._symm[4][self._ar_calls & 1][0]
 
-    def _allreduce_oneshot(self, sums):
-        """Sum over the ranks with onda_allreduce_oneshot: inputs in symmetric (peer-mapped) memory, two slots."""
-        import torch.distributed as dist
-        n = sums.numel()
-        world, rank = dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
-        slot_view = self._symm_slot(n, sums.device)
-        buf, hdl, _, slot_floats = self._symm
-        slot = self._ar_calls & 1
+    def _oneshot_args(self, sums):
+        """Stage ``sums`` in this call's symmetric slot (no copy when the fused pass wrote it there) and return
+        (rank, world, peer slot pointers, peer flag pointers, epoch) of the exchange."""
+        slot_view = self._symm_slot(sums.numel(), sums.device)
+        _, _, _, _, slots, rank, world = self._symm
+        _, bufs, flags = slots[self._ar_calls & 1]
         if sums.data_ptr() != slot_view.data_ptr():
             slot_view.copy_(sums)                       # input was produced elsewhere: stage it
         self._ar_calls += 1
-        ptr_t = nat.C.c_void_p * world
-        bufs = ptr_t(*[int(p) + 4 * slot * slot_floats for p in hdl.buffer_ptrs])
-        flags = ptr_t(*[int(p) + 4 * (2 * slot_floats + 32 * slot) for p in hdl.buffer_ptrs])
+        return rank, world, bufs, flags, self._ar_calls
+
+    def _allreduce_oneshot(self, sums):
+        """Sum over the ranks with onda_allreduce_oneshot: inputs in symmetric (peer-mapped) memory, two slots."""
+        rank, world, bufs, flags, epoch = self._oneshot_args(sums)
+        n = sums.numel()
         out = torch.empty((n,), dtype=torch.float32, device=sums.device)
-        nat.check(self._lib.onda_allreduce_oneshot(nat.ptr(out), n, rank, world, bufs, flags, self._ar_calls,
+        nat.check(self._lib.onda_allreduce_oneshot(nat.ptr(out), n, rank, world, bufs, flags, epoch,
                                                    _stream_ptr(sums.device)), "onda_allreduce_oneshot")
         return out
 
@@ -451,12 +461,6 @@ class prototype_handler:
         """Moving-average prototype update (:88-99).  In place; ``counter`` is untouched."""
         self._deferred_monitor = None
         sums, D, C, device = self._class_sums(feat, out)
-        sums = self._allreduce(sums)
-        if self.process_group is not None:       # the statistics tail is global (all ranks) only now
-            self._stats_src, self._stats_cache = (sums, C, D), None
-        if self._deferred_monitor is not None:
-            self._monitor_side_effects(self._deferred_monitor, self.last_stats)
-            self._deferred_monitor = None
         P, S, _ = self._state(device, False)
         if not isinstance(S, torch.Tensor):
             raise AttributeError("squared_mean is not initialised")
@@ -465,6 +469,29 @@ class prototype_handler:
         metric = self.distance_metric
         need_stats = metric == "mahalanobis"
         cnt = self.counter if isinstance(self.counter, torch.Tensor) else None
+        fused_exchange = (self.process_group is not None and self.allreduce == "oneshot" and sums.is_cuda
+                          and not (need_stats and cnt is None))
+        if fused_exchange:
+            # all-reduce + blend + next distance table in ONE launch: the kernel reads the peers' slots over NVLink
+            rank, world, bufs, flags, epoch = self._oneshot_args(sums)
+            reduced = self._buf(("reduced", epoch & 1), (sums.numel(),), torch.float32, device)
+            table = self._buf(("table", metric), (self._lib.onda_table_floats(C, D),), torch.float32, device, zero=True)
+            nat.check(self._lib.onda_ema_update_and_table_allreduce(
+                nat.ptr(P), nat.ptr(S), nat.ptr(cnt) if need_stats else None, nat.ptr(reduced), C, D,
+                float(self.ma_lambda), nat.METRIC[metric], nat.ptr(table), rank, world, bufs, flags, epoch,
+                _stream_ptr(device)), "onda_ema_update_and_table_allreduce")
+            sums = reduced
+        else:
+            sums = self._allreduce(sums)
+        if self.process_group is not None:       # the statistics tail is global (all ranks) only now
+            self._stats_src, self._stats_cache = (sums, C, D), None
+        if self._deferred_monitor is not None:
+            self._monitor_side_effects(self._deferred_monitor, self.last_stats)
+            self._deferred_monitor = None
+        if fused_exchange:
+            self._epoch += 1
+            self._table = {metric: (self._table_key(P, S, cnt, need_stats, device), table)}
+            return
         if need_stats and cnt is None:
             nat.check(self._lib.onda_ema_update(nat.ptr(P), nat.ptr(S), nat.ptr(sums), C, D, float(self.ma_lambda),
                                                 _stream_ptr(device)), "onda_ema_update")
