@@ -152,6 +152,15 @@ int onda_prior_mix_stats(const float* logits0, const float* logits1, const float
                          float coef0, float coef1, float coef2, int B, int C, int HW,
                          float* prior_out, float* stats_out, void* workspace, size_t workspace_bytes,
                          void* stream);
+
+/* Per-step log reductions of the method classes (framework/domain_adaptation/methods/prototypes.py:341-352), one
+ * launch: out4 = { number of pixels whose pseudo-label equals the first argmax over classes of student_logits
+ * [B, C, HW] (":346-347", labels [B*HW] int64, 255 never agrees), number of labels that are neither negative nor 255
+ * (":342"), sum of squared prototype entries (":351", divide by C*D for the mean), B*HW }.  Counts are exact.
+ * workspace: onda_step_log_workspace_bytes() bytes, zeroed once. */
+size_t onda_step_log_workspace_bytes(void);
+int onda_step_log_stats(const int64_t* labels, const float* student_logits, const float* prototypes, int B, int C, int HW,
+                        int D, float* out4, void* workspace, size_t workspace_bytes, void* stream);
 size_t onda_prior_workspace_bytes(int B, int C, int HW);
 
 /* ---- multi-GPU ---------------------------------------------------------------- */

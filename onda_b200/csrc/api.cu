@@ -412,6 +412,62 @@ __global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* _
     }
 }
 
+
+// ---- per-step log reductions (prototypes.py:341-352) ---------------------------------------------
+// agreement count of the pseudo-labels with the first argmax of the student logits, number of non-ignored labels,
+// sum of squared prototype entries.  Integer counts are exact; everything is combined in CTA order by the last CTA.
+constexpr int kLogSlots = 4;
+template <int CP>
+__global__ void __launch_bounds__(kPriorThreads) step_log_kernel(const long long* __restrict__ labels,
+                                                                 const float* __restrict__ logits,
+                                                                 const float* __restrict__ protos, int B, int C, int HW,
+                                                                 int n_proto, double* __restrict__ partials,
+                                                                 unsigned* __restrict__ ticket, float* __restrict__ out) {
+    __shared__ double red[kPriorThreads / 32][kLogSlots];
+    __shared__ bool last;
+    const long long N = (long long)B * HW;
+    double agree = 0.0, valid = 0.0, sq = 0.0;
+    for (long long n = (long long)blockIdx.x * kPriorThreads + threadIdx.x; n < N; n += (long long)gridDim.x * kPriorThreads) {
+        float z[CP];
+        load_pixel_row<CP>(logits, C, HW, n, z);
+        const long long lab = labels[n];
+        agree += lab == (long long)first_argmax<CP>(z, C) ? 1.0 : 0.0;      // == out.argmax(axis=1), :346-347
+        valid += (lab >= 0 && lab != 255) ? 1.0 : 0.0;                       // :342
+    }
+    for (int i = blockIdx.x * kPriorThreads + threadIdx.x; i < n_proto; i += gridDim.x * kPriorThreads) {
+        const double v = (double)protos[i];
+        sq += v * v;                                                         // (prototypes**2).mean(), :351
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v3[kLogSlots] = {agree, valid, sq, 0.0};
+#pragma unroll
+    for (int s = 0; s < kLogSlots; ++s) {
+        double v = v3[s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][s] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLogSlots) {
+        double v = 0.0;
+        for (int w = 0; w < kPriorThreads / 32; ++w) v += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * kLogSlots + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        if (threadIdx.x < kLogSlots) {
+            double v = 0.0;
+            for (unsigned c = 0; c < gridDim.x; ++c) v += __ldcg(partials + (size_t)c * kLogSlots + threadIdx.x);
+            out[threadIdx.x] = threadIdx.x == 3 ? (float)N : (float)v;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
 }  // namespace onda
 
 namespace onda {
@@ -683,6 +739,30 @@ int onda_prior_mix_stats(const float* logits0, const float* logits1, const float
     else
         prior_mix_kernel<32><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>(logits0, logits1, logits2, coef0, coef1, coef2, B,
                                                                                C, HW, prior_out, partials, ticket, stats_out);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+size_t onda_step_log_workspace_bytes(void) { return 256 + (size_t)4 * cached_sm_count() * kLogSlots * sizeof(double); }
+
+int onda_step_log_stats(const int64_t* labels, const float* student_logits, const float* prototypes, int B, int C, int HW,
+                        int D, float* out4, void* workspace, size_t workspace_bytes, void* stream) {
+    ONDA_REQUIRE(labels && student_logits && prototypes && out4 && workspace, "onda_step_log_stats: null pointer");
+    ONDA_REQUIRE(B > 0 && HW > 0 && D > 0 && C > 0 && C <= ONDA_MAX_CLASSES, "onda_step_log_stats: bad shape");
+    ONDA_REQUIRE(workspace_bytes >= onda_step_log_workspace_bytes(), "onda_step_log_stats: workspace too small");
+    const long long N = (long long)B * HW;
+    const int sms = cached_sm_count();
+    long long want = (N + kPriorThreads - 1) / kPriorThreads;
+    const int grid = (int)(want < 4LL * sms ? want : 4LL * sms);
+    unsigned* ticket = (unsigned*)workspace;  // zero on first use; the kernel re-arms it
+    double* partials = (double*)((char*)workspace + 256);
+    if (padded_classes(C) == 20)
+        step_log_kernel<20><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>((const long long*)labels, student_logits, prototypes, B, C,
+                                                                              HW, C * D, partials, ticket, out4);
+    else
+        step_log_kernel<32><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>((const long long*)labels, student_logits, prototypes, B, C,
+                                                                              HW, C * D, partials, ticket, out4);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;

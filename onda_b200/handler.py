@@ -31,6 +31,16 @@ def _stream_ptr(device):
     return nat.C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _CpuUnpickler(pickle.Unpickler):
+    """pickle.load for tensors that were saved from a CUDA device, on a machine without one."""
+
+    def find_class(self, module, name):
+        if module == "torch.storage" and name == "_load_from_bytes":
+            import io
+            return lambda b: torch.load(io.BytesIO(b), map_location="cpu", weights_only=False)
+        return super().find_class(module, name)
+
+
 class prototype_handler:
     """Class prototypes with distance-based pseudo-labelling and EMA / cumulative updates.
 
@@ -91,10 +101,25 @@ class prototype_handler:
             pickle.dump((self.prototypes, self.squared_mean, self.counter), f)
 
     def load(self, loc="prototypes.pickle"):
-        """Load the 3-tuple written by ``save``; returns False if the file is absent (:40-47)."""
+        """Load the 3-tuple written by ``save``; returns False if the file is absent (:40-47).
+
+        Also reads the legacy 2-tuple ``(prototypes, counter)`` of the ``prototypes.pickle`` shipped with the
+        reference (which the reference's own ``load`` cannot unpack): ``squared_mean`` then stays uninitialised, so
+        only the Euclidean metric works until ``append`` has rebuilt the state.  Tensors pickled on a CUDA device are
+        mapped to the CPU when no CUDA device is present.
+        """
         if os.path.exists(loc):
             with open(loc, "rb") as f:
-                self.prototypes, self.squared_mean, self.counter = pickle.load(f)
+                try:
+                    state = pickle.load(f)
+                except RuntimeError:          # CUDA storages without a CUDA device
+                    f.seek(0)
+                    state = _CpuUnpickler(f).load()
+            if len(state) == 2:
+                self.prototypes, self.counter = state
+                self.squared_mean = 0
+            else:
+                self.prototypes, self.squared_mean, self.counter = state
             print("Prototypes loaded!")
             return True
         return False
@@ -371,6 +396,39 @@ class prototype_handler:
         if prior is not None:
             prior = prior.view(shape) if len(shape) == 4 else prior[0].t()
         return prior, conf, host[3] * inv
+
+    def step_log_stats(self, pseudolabels, student_out):
+        """The per-step log reductions of the method classes (prototypes.py:341-352) in one launch.
+
+        ``pseudolabels``: (N, 1) / (N,) / (B, h, w) int64 with 255 = ignore; ``student_out``: (B, C, h, w) logits of
+        the model being trained.  Returns ``{"pseudolabel_pixel_num", "output & prototype agreement",
+        "mean_prototype_intensity_values"}`` as Python floats (the reference logs them, nothing reads them back).
+        """
+        self._require_cuda(pseudolabels, "pseudolabels")
+        logits3 = self._nchw(student_out, "student_out")
+        B, C, HW = logits3.shape
+        if pseudolabels.dtype != torch.int64 or pseudolabels.numel() != B * HW:
+            raise ValueError(f"pseudolabels must be int64 with {B * HW} entries, got {pseudolabels.dtype} {tuple(pseudolabels.shape)}")
+        self._require_cuda(self.prototypes, "prototypes")
+        device = logits3.device
+        P, _, _ = self._state(device, False)
+        labels = pseudolabels.contiguous()
+        out4 = torch.empty((4,), dtype=torch.float32, device=device)
+        wbytes = self._lib.onda_step_log_workspace_bytes()
+        work = self._buf("log_work", (wbytes,), torch.uint8, device, zero=True)
+        nat.check(self._lib.onda_step_log_stats(nat.ptr(labels), nat.ptr(logits3), nat.ptr(P), B, C, HW, P.shape[1],
+                                                nat.ptr(out4), nat.ptr(work), wbytes, _stream_ptr(device)),
+                  "onda_step_log_stats")
+        if self.process_group is not None:
+            import torch.distributed as dist
+            keep = out4[2].clone()                   # the prototypes are replicated, not sharded
+            dist.all_reduce(out4, op=dist.ReduceOp.SUM, group=self.process_group)
+            out4[2] = keep
+        agree, valid, sq, n = out4.tolist()
+        f32 = torch.tensor([agree, n, sq, float(P.numel())], dtype=torch.float32)
+        return {"pseudolabel_pixel_num": valid,
+                "output & prototype agreement": float(f32[0] / f32[1]),          # .float().mean() of exact 0/1 values
+                "mean_prototype_intensity_values": float(f32[2] / f32[3])}
 
     # ------------------------------------------------------------------ class sums and updates
     def _class_sums(self, feat, out):

@@ -442,6 +442,16 @@ def hybrid_prior(logits_ema, logits_static, logits_dynamic, monitor: OracleMonit
 # --------------------------------------------------------------------------
 # seeded synthetic inputs shared by tests and bench
 # --------------------------------------------------------------------------
+def step_log_stats(pseudolabels: torch.Tensor, student_out: torch.Tensor, protos: torch.Tensor) -> dict:
+    """The per-step log reductions, as written in framework/domain_adaptation/methods/prototypes.py:341-352."""
+    batch_size, _, w, h = student_out.shape
+    return {
+        "pseudolabel_pixel_num": float(((pseudolabels >= 0) * (pseudolabels != 255)).float().sum()),
+        "output & prototype agreement": float((pseudolabels.reshape(batch_size, w, h) == student_out.argmax(axis=1)).float().mean()),
+        "mean_prototype_intensity_values": float((protos ** 2).mean()),
+    }
+
+
 def synth_case(seed: int, b: int, d: int, h: int, w: int, c: int = 19, protos=None,
                counter=None, sharp: float = 4.0):
     """Cityscapes-shaped synthetic inputs: blocky label map, class-separable

@@ -95,3 +95,37 @@ def test_switch_logic_matches_reference_traces(tag):
     mon.eval(); n = len(mon.current_dict["prior static"]); mon.add({"prior static": 0.5})
     assert len(mon.current_dict["prior static"]) == n
     assert static_share(0.9, False, 0.85) == 1 and static_share(0.8, False, 0.85) == 0
+
+
+def test_load_reads_three_tuple_and_legacy_two_tuple(tmp_path):
+    """save/load keep the reference's 3-tuple pickle (prototype_handler.py:37-47); the legacy 2-tuple shipped as
+    prototypes.pickle (prototypes, counter) loads too, with squared_mean left uninitialised."""
+    import pickle
+    from onda_b200 import prototype_handler
+    P, S, c = torch.randn(19, 8), torch.rand(19, 8) + 1, torch.arange(19.0)
+    h = prototype_handler()
+    h.prototypes, h.squared_mean, h.counter = P, S, c
+    loc = str(tmp_path / "state.pickle")
+    h.save(loc)
+    assert [torch.equal(a, b) for a, b in zip(pickle.load(open(loc, "rb")), (P, S, c))] == [True] * 3
+    h2 = prototype_handler()
+    assert h2.load(loc) and torch.equal(h2.prototypes, P) and torch.equal(h2.squared_mean, S) and torch.equal(h2.counter, c)
+    legacy = str(tmp_path / "legacy.pickle")
+    pickle.dump((P, c), open(legacy, "wb"))
+    h3 = prototype_handler()
+    assert h3.load(legacy) and torch.equal(h3.prototypes, P) and torch.equal(h3.counter, c)
+    assert isinstance(h3.squared_mean, int) and h3.squared_mean == 0
+    assert not prototype_handler().load(str(tmp_path / "absent.pickle"))
+
+
+def test_oracle_step_log_stats_small_case():
+    """The restated log reductions on a hand-checkable case (prototypes.py:341-352)."""
+    from oracle import proto_oracle as po
+    labels = torch.tensor([[0], [1], [255], [2]])
+    out = torch.zeros(1, 3, 2, 2)
+    out[0, 0, 0, 0] = 1      # pixel 0 -> class 0 (agrees)
+    out[0, 2, 0, 1] = 1      # pixel 1 -> class 2 (label 1: disagrees)
+    out[0, 1, 1, 0] = 1      # pixel 2 -> class 1 (label 255: never agrees)
+    out[0, 2, 1, 1] = 1      # pixel 3 -> class 2 (agrees)
+    got = po.step_log_stats(labels, out, torch.tensor([[1.0, 2.0], [3.0, 4.0]]))
+    assert got == {"pseudolabel_pixel_num": 3.0, "output & prototype agreement": 0.5, "mean_prototype_intensity_values": 7.5}

@@ -431,3 +431,68 @@ def test_tau_regularisation_side_effect():
     mon.eval()
     h.pseudo_labels(feat, prior, confidence_monitor=mon)
     assert h.tau == pytest.approx(1.001)                        # frozen monitor: no side effects
+
+
+LABEL_MAPS = ["one_class", "two_classes_odd_split", "aligned_runs_of_32", "stripes_of_5", "random", "ragged_tail"]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("kind", LABEL_MAPS)
+def test_class_sums_for_label_maps(kind, impl):
+    """Class sums / counts for label maps that stress the summation scheme of the tensor-core kernel: classes that span
+    one, two or all four 32-entry ranges of a tile's class-sorted order (head partials), runs that end exactly on a
+    range boundary, and a last tile with fewer than 128 pixels.  Tolerance 1e-5 * max|ref|; counts exact."""
+    D, C = 256, 19
+    need_shape(impl, D, C)
+    B, h, w = (1, 8, 16 * 3) if kind != "ragged_tail" else (1, 7, 53)       # 384 px = 3 full tiles; 371 px = ragged
+    n = B * h * w
+    g = torch.Generator().manual_seed(77)
+    if kind == "one_class":
+        y = torch.full((n,), 3)
+    elif kind == "two_classes_odd_split":
+        y = torch.where(torch.arange(n) % 128 < 71, 5, 11)
+    elif kind == "aligned_runs_of_32":
+        y = (torch.arange(n) // 32) % C
+    elif kind == "stripes_of_5":
+        y = (torch.arange(n) // 5) % C
+    else:
+        y = torch.randint(0, C, (n,), generator=g)
+    y = y[torch.randperm(n, generator=g)] if kind in ("two_classes_odd_split", "stripes_of_5") else y
+    out = torch.randn(n, C, generator=g) * 0.1
+    out[torch.arange(n), y] += 5.0
+    out = out.reshape(B, h, w, C).permute(0, 3, 1, 2).contiguous()
+    feat = torch.randn(B, D, h, w, generator=g) * 2.0 + 0.3
+    case = po.synth_case(5, 1, D, 4, 4, c=C)
+    hd = make_handler(case["protos"], case["sq_mean"], case["counter"], "mahalanobis", impl=impl)
+    sums, cnt = hd.get_proto_array(feat.to(dev()), out.to(dev()))
+    ref_s, ref_c = po.class_sums(feat, out)
+    assert torch.equal(cnt.cpu(), ref_c)
+    assert (sums.cpu() - ref_s).abs().max() <= 1e-5 * ref_s.abs().max()
+    # the squared sums go through ma(): compare the blended state
+    o = make_oracle(case["protos"], case["sq_mean"], case["counter"], "mahalanobis")
+    prior = torch.full((B, C, h, w), 1.0 / C)
+    hd.pseudo_labels_fused(feat.to(dev()), prior.to(dev()), out.to(dev()))
+    hd.ma(feat.to(dev()), out.to(dev()))
+    o.ma(feat, out)
+    assert (hd.prototypes.cpu() - o.prototypes).abs().max() <= 1e-5 * o.prototypes.abs().max()
+    assert (hd.squared_mean.cpu() - o.squared_mean).abs().max() <= 1e-5 * o.squared_mean.abs().max()
+
+
+def test_step_log_stats_match_reference_expressions():
+    """prototypes.py:341-352 -- agreement with the student's argmax, non-ignored label count, mean squared prototype.
+    Counts are exact (so the fp32 mean of 0/1 values is bit-identical); the prototype mean within 1e-6 relative."""
+    case = po.synth_case(21, 3, 64, 9, 14)
+    hd = make_handler(case["protos"], case["sq_mean"], case["counter"], "mahalanobis")
+    o = make_oracle(case["protos"], case["sq_mean"], case["counter"], "mahalanobis")
+    labels = hd.pseudo_labels(case["feat"].to(dev()), case["prior"].to(dev()))
+    ref_labels = o.pseudo_labels(case["feat"], case["prior"])
+    g = torch.Generator().manual_seed(3)
+    student = case["out"] + torch.randn(case["out"].shape, generator=g) * 2.0
+    got = hd.step_log_stats(labels, student.to(dev()))
+    want = po.step_log_stats(labels.cpu(), student, case["protos"])
+    assert got["pseudolabel_pixel_num"] == want["pseudolabel_pixel_num"]
+    assert got["output & prototype agreement"] == want["output & prototype agreement"]
+    assert abs(got["mean_prototype_intensity_values"] - want["mean_prototype_intensity_values"]) <= 1e-6 * want["mean_prototype_intensity_values"]
+    assert 0 < got["pseudolabel_pixel_num"] < labels.numel() and torch.equal(labels.cpu(), ref_labels)
+    with pytest.raises(ValueError):
+        hd.step_log_stats(labels[:5], student.to(dev()))
