@@ -119,6 +119,12 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
 __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
     uint64_t v;
     asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
@@ -166,23 +172,23 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr) : "memory");
 }
 
-// x[J] = feature at plane J of a pixel: the address is one IMAD.WIDE with an immediate plane index (no table of
-// offsets in registers, no dependent chain), the load bypasses L1 allocation (streamed once)
+// x[J] = feature at plane J of a pixel: 32-bit element index off0 + J * plane (one IMAD with an immediate plane index,
+// no table of offsets in registers, no dependent chain), then one IMAD.WIDE onto the base; the load bypasses L1
+// allocation (streamed once)
 template <int J>
-__device__ __forceinline__ float ldg_plane(unsigned long long src, unsigned plane_bytes) {
+__device__ __forceinline__ float ldg_plane(const float* feat, unsigned off0, unsigned plane) {
     float v;
-    asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, %3, %1;\n\tld.global.nc.L1::no_allocate.f32 %0, [a];\n\t}"
-                 : "=f"(v) : "l"(src), "r"(plane_bytes), "n"(J));
+    const float* a = feat + (off0 + (unsigned)J * plane);      // 32-bit element index (tc_supported: the map has < 2^32 elements)
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(a));
     return v;
 }
 template <int N, int... Js>
-__device__ __forceinline__ void ldg_planes(float (&x)[N], unsigned long long src, unsigned plane_bytes, std::integer_sequence<int, Js...>) {
-    ((x[Js] = ldg_plane<Js>(src, plane_bytes)), ...);
+__device__ __forceinline__ void ldg_planes(float (&x)[N], const float* feat, unsigned off0, unsigned plane, std::integer_sequence<int, Js...>) {
+    ((x[Js] = ldg_plane<Js>(feat, off0, plane)), ...);
 }
-
 template <int J0, int N, int... Js>
-__device__ __forceinline__ void ldg_planes_part(float (&x)[N], unsigned long long src, unsigned plane_bytes, std::integer_sequence<int, Js...>) {
-    ((x[J0 + Js] = ldg_plane<J0 + Js>(src, plane_bytes)), ...);
+__device__ __forceinline__ void ldg_planes_part(float (&x)[N], const float* feat, unsigned off0, unsigned plane, std::integer_sequence<int, Js...>) {
+    ((x[J0 + Js] = ldg_plane<J0 + Js>(feat, off0, plane)), ...);
 }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100)
@@ -226,7 +232,7 @@ __host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
     s.w = o; o += (size_t)D * 4;
     s.bhi = o; o += (size_t)32 * D * 4;
     s.blo = o; o += (size_t)32 * D * 4;
-    s.acc = o; o += sums ? (size_t)2 * (C * D + kTcHeadFloats) * 4 : 0;   // [sum | sum of squares] x [C class rows of D | head partials]
+    s.acc = o; o += sums ? (size_t)2 * (C * D + kTcHeadFloats) * 4 : 0;   // [class * D/32 + chunk | then 3 heads per group][sum | sum of squares][32 channels]
     s.total = o;
     return s;
 }
@@ -314,16 +320,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         const uint32_t tg_lane = smem_u32(Tg) + 4u * lane;           // class sums: lane = channel of the chunk
         const int gbar = 3 + group;                                   // named barrier of the group (128 threads)
         float x[kTcChunkC];
-        const unsigned plane = HWu * (unsigned)sizeof(float);
+        const unsigned plane = HWu;
         auto load_base = [&](int q) {   // address of channel b*32 of this lane's pixel in chunk q
             const int t = q >> nb_shift, b = q & (NB - 1);
             const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
             unsigned n = tile * kTilePixels + 32 * quarter + lane;
             n = n < Nu ? n : Nu - 1;         // clamp: results of padded rows are never stored (epilogue / sorter guard them)
             const unsigned bimg = n / HWu, pix = n - bimg * HWu;
-            return reinterpret_cast<unsigned long long>(p.feat + ((size_t)bimg * D + (size_t)b * kTcChunkC) * HWu + pix);
+            return (bimg * (unsigned)D + (unsigned)(b * kTcChunkC)) * HWu + pix;
         };
-        auto issue_loads = [&](int q) { ldg_planes(x, load_base(q), plane, std::make_integer_sequence<int, kTcChunkC>{}); };
+        auto issue_loads = [&](int q) { ldg_planes(x, p.feat, load_base(q), plane, std::make_integer_sequence<int, kTcChunkC>{}); };
         if (group < total_chunks) issue_loads(group);
         for (int q = group; q < total_chunks; q += kTcGroups) {
             const int t = q >> nb_shift, b = q & (NB - 1);
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             tc_fence_after();
             const long long t_cv0 = prof ? clock64() : 0;
             const bool more = q + kTcGroups < total_chunks;
-            const unsigned long long nsrc = more ? load_base(q + kTcGroups) : 0ull;
+            const unsigned nsrc = load_base(more ? q + kTcGroups : q);
             uint64_t a2 = 0;                       // sum_j w_j x'_j^2 of the even / odd channels (packed f32x2 math)
             const uint32_t tcol = tmem_base + lane_base + (uint32_t)group * 64;
             const ulonglong2* mu4 = reinterpret_cast<const ulonglong2*>(mus + b * kTcChunkC);     // -mu, two pairs per load
@@ -372,8 +378,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 tc_st8(tcol + part * 8, hi);
                 tc_st8(tcol + 32 + part * 8, lo);
                 if (more) {   // the registers of channels 0..15 are free again: their next loads start here
-                    if (part == 1) ldg_planes_part<0>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
-                    if (part == 3) ldg_planes_part<8>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                    if (part == 1) ldg_planes_part<0>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                    if (part == 3) ldg_planes_part<8>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 8>{});
                 }
             }
             const float a = __uint_as_float((uint32_t)a2) + __uint_as_float((uint32_t)(a2 >> 32));
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             // the batches of the summation: 32 back-to-back loads from every warp of a group fill the SM's miss queue and
             // the warp would sit blocked at the issue (measured: a quarter of the worker's time).
             if (!SUMS && more) {
-                ldg_planes_part<16>(x, nsrc, plane, std::make_integer_sequence<int, 16>{});
+                ldg_planes_part<16>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 16>{});
             }
             if (prof) {
                 dbg[5] += t_cv1 - t_cv0;                 // centring / splitting / tcgen05.st issue
@@ -410,23 +416,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 const int* eo = eoff + par * kTilePixels;
                 const int* ec = ecls + par * kTilePixels;
                 const int* ct = cuts + par * 8;
-                const int stat_stride = C * D + kTcHeadFloats;
-                float* a1 = acc + b * kTcChunkC + lane;
-                float* a2 = a1 + stat_stride;
-                const int head_base = C * D + group * 3 * kTcChunkC - b * kTcChunkC;    // head j of this group, relative to a1: + (j-1)*32
+                // accumulators: row (class * NB + b), then [sum | sum of squares][32 channels]: the pair of a flush is 128 bytes apart
+                const uint32_t a1 = smem_u32(acc) + (uint32_t)(b * 64 + lane) * 4u;     // + row offset of the class (bytes, from the sorter)
+                const uint32_t head_base = (uint32_t)(C * NB + group * 3 - b) * 256u;   // head j of this group, relative to a1: + (j-1)*256
                 const int idx = 32 * quarter + lane;                                    // this warp's range: entries 32*quarter .. +31
                 int nlive = ct[0] - 32 * quarter;                                       // ct[0] = live entries of the tile
                 nlive = nlive < 0 ? 0 : (nlive > 32 ? 32 : nlive);
                 const int eo_i = eo[idx], er_i = ec[idx];
                 const unsigned endbits = __ballot_sync(0xffffffffu, eo_i & 1);          // segment ends (sorter: class end or entry 31)
                 const int myoff = eo_i & ~1;
-                const int myrow = er_i < 0 ? head_base + (quarter - 1) * kTcChunkC : er_i;    // accumulator row of this entry's segment
+                const uint32_t myrow = er_i < 0 ? head_base + (uint32_t)(quarter - 1) * 256u : (uint32_t)er_i;   // accumulator row (bytes) of this entry's segment
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int e0 = 0; e0 < 32; e0 += 8) {
                     if (more) {
-                        if (e0 == 0) ldg_planes_part<16>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
-                        if (e0 == 16) ldg_planes_part<24>(x, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                        if (e0 == 0) ldg_planes_part<16>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 8>{});
+                        if (e0 == 16) ldg_planes_part<24>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 8>{});
                     }
                     if (e0 >= nlive) continue;
                     float xv[8];
@@ -442,9 +447,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                         s1 += xv[e];
                         s2 = fmaf(xv[e], xv[e], s2);
                         if (endbits & (1u << (e0 + e))) {
-                            const int r = __shfl_sync(0xffffffffu, myrow, e0 + e);
-                            a1[r] += s1;
-                            a2[r] += s2;
+                            const uint32_t ad = a1 + __shfl_sync(0xffffffffu, myrow, e0 + e);
+                            sts32(ad, lds32(ad) + s1);
+                            sts32(ad + 128u, lds32(ad + 128u) + s2);
                             s1 = 0.f;
                             s2 = 0.f;
                         }
@@ -459,11 +464,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                         const int j = __ffs(m) - 1;
                         m &= m - 1;
                         const int k = __shfl_sync(0xffffffffu, hj, j) & 0xff;
-                        const int hrow = head_base + (j - 1) * kTcChunkC;
-                        a1[k * D] += a1[hrow];
-                        a2[k * D] += a2[hrow];
-                        a1[hrow] = 0.f;
-                        a2[hrow] = 0.f;
+                        const uint32_t hd = a1 + head_base + (uint32_t)(j - 1) * 256u, ad = a1 + (uint32_t)(k * NB) * 256u;
+                        sts32(ad, lds32(ad) + lds32(hd));
+                        sts32(ad + 128u, lds32(ad + 128u) + lds32(hd + 128u));
+                        sts32(hd, 0.f);
+                        sts32(hd + 128u, 0.f);
                     }
                 }
                 if (q + kTcGroups >= total_chunks || ((q + kTcGroups) >> nb_shift) != t) {   // last chunk of this tile for the group
@@ -628,7 +633,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 const bool seg_end = valid && (pos == cs + ct_ - 1 || (pos & 31) == 31);      // last of its class, or of its range
                 const bool in_head = valid && cs < (pos & ~31);                                // the class began in an earlier range
                 eoff[par * kTilePixels + pos] = ((32 * v + lane) * (kTcTRow * 4)) | (seg_end ? 1 : 0);   // row offset (even) | end flag
-                ecls[par * kTilePixels + pos] = in_head ? -1 : y[r] * D;                       // accumulator row, -1 = the range's head
+                ecls[par * kTilePixels + pos] = in_head ? -1 : y[r] * NB * 256;                // accumulator row offset (bytes), -1 = the range's head
             }
             if (sw == 0) {
                 if (lane < 4) cuts[par * 8 + lane] = lane == 0 ? n_valid : (lane == 1 ? cutcls[1] : (lane == 2 ? cutcls[2] : cutcls[3]));
@@ -650,7 +655,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     if (SUMS) {
         float* out = p.cta_partials + (size_t)blockIdx.x * sums_floats(C, D);
         const int cd = C * D;
-        for (int i = tid; i < 2 * cd; i += kTcThreads) out[i] = i < cd ? acc[i] : acc[kTcHeadFloats + i];
+        for (int i = tid; i < 2 * cd; i += kTcThreads) {     // out: [sum | sum of squares][class][D]
+            const int stat = i >= cd, rem = i - stat * cd, k = rem / D, j = rem - k * D;
+            out[i] = acc[((k * NB + (j >> 5)) * 2 + stat) * 32 + (j & 31)];
+        }
         if (tid < C) out[(size_t)2 * C * D + tid] = (float)cnt[tid];
     }
     if (warp == kTcMmaWarp) {
@@ -661,7 +669,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
 
 // ---- host side -----------------------------------------------------------------------------------------
 bool tc_supported(int B, int D, int HW, int C) {
-    (void)B; (void)HW;
+    if ((unsigned long long)B * D * HW >= (1ull << 32)) return false;            // 32-bit element offsets in the workers
     if (!(D % 128 == 0 && D >= 128 && D <= 256 && C >= 1 && C <= 32)) return false;   // D/64 block pairs: 2 or 4
     return tc_smem(D, C, padded_classes(C), true).total <= 227 * 1024;   // per-CTA shared-memory limit on sm_100
 }
