@@ -267,13 +267,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     auto acc_empty = [&](int i) { return bars + 8u * (2 * kTcGroups + 2 + i); };
     auto sort_ready = [&](int i) { return bars + 8u * (2 * kTcGroups + 4 + i); };
     auto sort_free = [&](int i) { return bars + 8u * (2 * kTcGroups + 6 + i); };
+    const uint32_t btab_bar = bars + 8u * (2 * kTcGroups + 8);
 
     const TableLayout T = table_layout(C, D);
     // ---- one-time setup: tables to shared memory, barriers, tensor memory
-    for (int i = tid; i < 32 * D; i += kTcThreads) {
-        Bhi[i] = p.table[T.off_qhi + i];
-        Blo[i] = p.table[T.off_qlo + i];
-    }
     for (int i = tid; i < D; i += kTcThreads) {
         mus[i] = -p.table[T.off_mu + i];      // negated: the workers centre with a packed add
         wsm[i] = p.table[T.off_w + i];
@@ -293,7 +290,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             mbar_init(sort_ready(i), 64);
             mbar_init(sort_free(i), kTcWorkerWarps);
         }
+        mbar_init(btab_bar, 1);
         fence_barrier_init();
+        // B operand tables (hi | lo, adjacent in the table and in shared memory): one bulk asynchronous copy, off
+        // everybody's critical path -- only the MMA issuer waits for it, before its first MMA
+        const uint32_t bytes = (uint32_t)(2 * 32 * D) * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(btab_bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(Bhi)), "l"(p.table + T.off_qhi), "r"(bytes), "r"(btab_bar) : "memory");
     }
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
@@ -481,6 +485,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(128, 32);
             const uint32_t bhi_addr = smem_u32(Bhi), blo_addr = smem_u32(Blo);
+            mbar_wait<32>(btab_bar, 0);             // the B tables have landed (bulk copy of the prologue)
             for (int t = 0; t < my_tiles; ++t) {
                 const int par = t & 1;
                 if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
