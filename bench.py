@@ -221,11 +221,42 @@ def run_onda(args):
     for i in range(args.warmup):
         step(i)
     barrier()
+    # Kernel time first, in a short eager loop: CUDA events recorded by the library around every 4th launch of the
+    # dominant kernel (not possible inside a captured graph).
+    lib.onda_kernel_timing_enable(4)
+    for i in range(max(8, min(args.steps, 24))):
+        step(i)
+    torch.cuda.synchronize()
+    tot_ms, n_timed = nat.C.c_float(0), nat.C.c_int(0)
+    nat.check(lib.onda_kernel_timing_read(nat.C.byref(tot_ms), nat.C.byref(n_timed)))
+    lib.onda_kernel_timing_enable(0)
+    # The timed steps replay CUDA graphs (one per rotating input set; SURVEY 8d: "graph-replayed steps") on one GPU:
+    # the step is three launches, and at small batch the host cannot enqueue them as fast as the GPU runs them.
+    # Multi-GPU steps stay eager (the one-shot exchange takes a fresh epoch argument per call).
+    eager_step, graphs, launches_per_step = step, None, None
+    if world == 1 and args.graph:
+        try:
+            l0 = lib.onda_launch_count()
+            graphs = []
+            for k in range(len(sets)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    eager_step(k)
+                graphs.append(g)
+            launches_per_step = (lib.onda_launch_count() - l0) // len(sets)
+
+            def step(i):
+                graphs[i % len(graphs)].replay()
+            for i in range(args.warmup):
+                step(i)
+        except Exception as exc:           # capture unavailable: measure the eager loop and say so
+            print(f"[bench] CUDA graph capture failed ({exc!r}); timing the eager loop", file=sys.stderr)
+            graphs, step = None, eager_step
+    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    lib.onda_kernel_timing_enable(4)      # CUDA events around every 4th launch of the dominant kernel (small probe effect)
     launches0 = lib.onda_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -239,10 +270,8 @@ def run_onda(args):
     barrier()
     t_wall1 = time.time()
     ms = e0.elapsed_time(e1)
-    launches = lib.onda_launch_count() - launches0
-    tot_ms, n_timed = nat.C.c_float(0), nat.C.c_int(0)
-    nat.check(lib.onda_kernel_timing_read(nat.C.byref(tot_ms), nat.C.byref(n_timed)))
-    lib.onda_kernel_timing_enable(0)
+    launches = lib.onda_launch_count() - launches0 if graphs is None else launches_per_step * args.steps
+    step = eager_step
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     t = torch.tensor([ms], device=device)
     if world > 1:
@@ -307,7 +336,9 @@ def run_onda(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "host_enqueue_ms_per_step": host_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(d, world, args.allreduce),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(d, world, args.allreduce),
+                       launch="CUDA graph replay (one graph per input set)" if graphs is not None else "eager launches"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps},
@@ -341,6 +372,8 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--allreduce", default="oneshot", choices=["nccl", "oneshot"],
                     help="exchange of the class-sum buffer at N>1: NCCL all_reduce or the library's one-shot NVLink kernel")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="time eager launches instead of CUDA-graph replays (single-GPU runs replay graphs by default)")
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (default 32 = the bench workload)")
     ap.add_argument("--label-block", type=int, default=8, help="side of the constant-label blocks of the synthetic maps")
     ap.add_argument("--logit-margin", type=float, default=4.0, help="logit bonus of the block's label (coherence of the argmax)")
