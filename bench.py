@@ -232,9 +232,10 @@ def run_onda(args):
     lib.onda_kernel_timing_enable(0)
     # The timed steps replay CUDA graphs (one per rotating input set; SURVEY 8d: "graph-replayed steps") on one GPU:
     # the step is three launches, and at small batch the host cannot enqueue them as fast as the GPU runs them.
-    # Multi-GPU steps stay eager (the one-shot exchange takes a fresh epoch argument per call).
+    # Multi-GPU: the exchange fused into ma() keeps its epoch in device memory, so those steps replay too (the two
+    # graphs alternate strictly, like the two peer-visible slots); the NCCL variant stays eager.
     eager_step, graphs, launches_per_step = step, None, None
-    if world == 1 and args.graph:
+    if args.graph and (world == 1 or args.allreduce == "oneshot"):
         try:
             l0 = lib.onda_launch_count()
             graphs = []

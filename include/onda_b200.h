@@ -183,11 +183,13 @@ int onda_allreduce_oneshot(float* out, size_t n, int rank, int world, void* cons
  * handshake of the one-shot all-reduce, reads the peers' slots over NVLink, adds them in rank order while it blends
  * (prototype_handler.py:88-99) and rebuilds the distance table, and writes the reduced buffer to sums_out
  * (onda_sums_floats(C, D) floats: the statistics tail is global afterwards).  Same slot / flag / epoch rules as
- * onda_allreduce_oneshot. */
+ * onda_allreduce_oneshot.  If epoch_counter (device, one uint32 per slot, initialised to the same non-zero value
+ * on every rank) is given, the epoch is read from it and incremented by the kernel, and `epoch` is ignored: the
+ * call can then be captured in a CUDA graph and replayed. */
 int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, const float* counter, float* sums_out,
                                         int C, int D, float ma_lambda, int metric, float* table, int rank, int world,
                                         void* const* peer_bufs_host, void* const* peer_flags_host, uint32_t epoch,
-                                        void* stream);
+                                        uint32_t* epoch_counter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
                                                               const float* __restrict__ cnt, int C, int D, int metric,
                                                               float* __restrict__ table, const float* __restrict__ sums,
                                                               float lam, PeerTable peers, int rank, int world,
-                                                              uint32_t epoch, float* __restrict__ sums_out) {
+                                                              uint32_t epoch, float* __restrict__ sums_out,
+                                                              uint32_t* __restrict__ epoch_counter) {
     // world > 0: `sums` of every rank sit in peer-mapped slots; this kernel is also the all-reduce -- handshake,
     // then every use of sums[i] is the rank-ordered sum over the peers (identical on every rank), and the reduced
     // buffer is written to sums_out for the statistics readers.
@@ -88,6 +89,9 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
     const bool mahal = metric == ONDA_METRIC_MAHALANOBIS;
     const bool gather = world > 0;
     __shared__ float cn[32];               // pixel count of every class (the EMA's cnt_k)
+    // the epoch of this exchange: a host argument, or (graph replay: arguments are frozen) a device counter that the
+    // last CTA of this grid bumps for the next call
+    if (gather && epoch_counter != nullptr) epoch = *reinterpret_cast<volatile uint32_t*>(epoch_counter);
     if (gather) peer_handshake(peers, rank, world, epoch);
     __shared__ float gs[2 * 32 * 32];      // gather: the reduced (sum | sum of squares)[class][this CTA's 32 channels]
     if (gather) {
@@ -238,7 +242,10 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
         double v = 0.0;
         for (unsigned c = 0; c < gridDim.x; ++c) v += __ldcg(part + (size_t)c * 32 + threadIdx.x);
         table[T.off_bias + threadIdx.x] = (float)v;
-        if (threadIdx.x == 0) *ticket = 0u;        // re-arm for the next build
+        if (threadIdx.x == 0) {
+            *ticket = 0u;        // re-arm for the next build
+            if (gather && epoch_counter != nullptr) *epoch_counter = epoch + 1u;     // every CTA has read it by now
+        }
     }
 }
 
@@ -568,7 +575,7 @@ int onda_build_distance_table(const float* prototypes, const float* squared_mean
     if (metric == ONDA_METRIC_MAHALANOBIS)
         ONDA_REQUIRE(squared_mean && counter, "onda_build_distance_table: mahalanobis needs squared_mean and counter");
     table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(const_cast<float*>(prototypes), const_cast<float*>(squared_mean), counter, C, D, metric,
-                                                                                   table, nullptr, 0.f, PeerTable{}, 0, 0, 0u, nullptr);
+                                                                                   table, nullptr, 0.f, PeerTable{}, 0, 0, 0u, nullptr, nullptr);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
@@ -673,7 +680,7 @@ int onda_ema_update_and_table(float* prototypes, float* squared_mean, const floa
                  "onda_ema_update_and_table: unexpected value for attribute distance_metric (%d)", metric);
     if (metric == ONDA_METRIC_MAHALANOBIS) ONDA_REQUIRE(counter, "onda_ema_update_and_table: mahalanobis needs counter");
     table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
-                                                                                   table, sums, ma_lambda, PeerTable{}, 0, 0, 0u, nullptr);
+                                                                                   table, sums, ma_lambda, PeerTable{}, 0, 0, 0u, nullptr, nullptr);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
@@ -682,7 +689,7 @@ int onda_ema_update_and_table(float* prototypes, float* squared_mean, const floa
 int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, const float* counter, float* sums_out,
                                         int C, int D, float ma_lambda, int metric, float* table, int rank, int world,
                                         void* const* peer_bufs_host, void* const* peer_flags_host, uint32_t epoch,
-                                        void* stream) {
+                                        uint32_t* epoch_counter, void* stream) {
     ONDA_REQUIRE(prototypes && squared_mean && sums_out && table && peer_bufs_host && peer_flags_host,
                  "onda_ema_update_and_table_allreduce: null pointer");
     ONDA_REQUIRE(C > 0 && C <= ONDA_MAX_CLASSES && D > 0, "onda_ema_update_and_table_allreduce: unsupported shape C=%d D=%d", C, D);
@@ -690,12 +697,12 @@ int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, 
                  "onda_ema_update_and_table_allreduce: unexpected value for attribute distance_metric (%d)", metric);
     if (metric == ONDA_METRIC_MAHALANOBIS) ONDA_REQUIRE(counter, "onda_ema_update_and_table_allreduce: mahalanobis needs counter");
     ONDA_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "onda_ema_update_and_table_allreduce: bad rank %d / world %d", rank, world);
-    ONDA_REQUIRE(epoch != 0, "onda_ema_update_and_table_allreduce: epoch 0 is the flags' initial value");
+    ONDA_REQUIRE(epoch != 0 || epoch_counter, "onda_ema_update_and_table_allreduce: epoch 0 is the flags' initial value");
     for (int r = 0; r < world; ++r)
         ONDA_REQUIRE(peer_bufs_host[r] && peer_flags_host[r], "onda_ema_update_and_table_allreduce: null peer pointer for rank %d", r);
     const PeerTable peers = make_peer_table(rank, world, peer_bufs_host, peer_flags_host);
     table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
-                                                                                   table, nullptr, ma_lambda, peers, rank, world, epoch, sums_out);
+                                                                                   table, nullptr, ma_lambda, peers, rank, world, epoch, sums_out, epoch_counter);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;

@@ -480,9 +480,13 @@ class prototype_handler:
             view = buf[slot * slot_floats: slot * slot_floats + n]
             bufs = ptr_t(*[p + 4 * slot * slot_floats for p in peer_ptrs])
             flags = ptr_t(*[p + 4 * (2 * slot_floats + 32 * slot) for p in peer_ptrs])
-            slots.append((view, bufs, flags))
+            flags_fused = ptr_t(*[p + 4 * (2 * slot_floats + 32 * slot + 8) for p in peer_ptrs])   # own words: own epochs
+            slots.append((view, bufs, flags, flags_fused))
         self._symm = (buf, hdl, n, slot_floats, slots, rank, world)
         self._ar_calls = 0
+        # epochs of the exchange fused into ma(): one device counter per slot, bumped by the kernel itself, so the
+        # call has no per-step host argument and can be replayed from a CUDA graph
+        self._epoch_ctr = torch.ones((2,), dtype=torch.int32, device=device)
 
     def _symm_slot(self, n, device):
         """The peer-visible input slot of the next one-shot all-reduce (two slots, alternating per call)."""
@@ -490,15 +494,19 @@ class prototype_handler:
             self._symm_init(n, device)
         return self._symm[4][self._ar_calls & 1][0]
 
-    def _oneshot_args(self, sums):
+    def _oneshot_args(self, sums, fused=False):
         """Stage ``sums`` in this call's symmetric slot (no copy when the fused pass wrote it there) and return
-        (rank, world, peer slot pointers, peer flag pointers, epoch) of the exchange."""
+        (rank, world, peer slot pointers, peer flag pointers, epoch) of the exchange; for the exchange fused into
+        ``ma`` the last item is the device pointer of the slot's epoch counter instead."""
         slot_view = self._symm_slot(sums.numel(), sums.device)
         _, _, _, _, slots, rank, world = self._symm
-        _, bufs, flags = slots[self._ar_calls & 1]
+        slot = self._ar_calls & 1
+        _, bufs, flags, flags_fused = slots[slot]
         if sums.data_ptr() != slot_view.data_ptr():
             slot_view.copy_(sums)                       # input was produced elsewhere: stage it
         self._ar_calls += 1
+        if fused:
+            return rank, world, bufs, flags_fused, self._epoch_ctr.data_ptr() + 4 * slot
         return rank, world, bufs, flags, self._ar_calls
 
     def _allreduce_oneshot(self, sums):
@@ -531,12 +539,12 @@ class prototype_handler:
                           and not (need_stats and cnt is None))
         if fused_exchange:
             # all-reduce + blend + next distance table in ONE launch: the kernel reads the peers' slots over NVLink
-            rank, world, bufs, flags, epoch = self._oneshot_args(sums)
-            reduced = self._buf(("reduced", epoch & 1), (sums.numel(),), torch.float32, device)
+            rank, world, bufs, flags, epoch_ctr = self._oneshot_args(sums, fused=True)
+            reduced = self._buf(("reduced", self._ar_calls & 1), (sums.numel(),), torch.float32, device)
             table = self._buf(("table", metric), (self._lib.onda_table_floats(C, D),), torch.float32, device, zero=True)
             nat.check(self._lib.onda_ema_update_and_table_allreduce(
                 nat.ptr(P), nat.ptr(S), nat.ptr(cnt) if need_stats else None, nat.ptr(reduced), C, D,
-                float(self.ma_lambda), nat.METRIC[metric], nat.ptr(table), rank, world, bufs, flags, epoch,
+                float(self.ma_lambda), nat.METRIC[metric], nat.ptr(table), rank, world, bufs, flags, 0, epoch_ctr,
                 _stream_ptr(device)), "onda_ema_update_and_table_allreduce")
             sums = reduced
         else:

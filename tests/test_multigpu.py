@@ -76,3 +76,64 @@ def test_sharded_matches_single_gpu(mode):
     per_rank = [l0.view(4, -1), l1.view(4, -1)]
     sharded = torch.cat([torch.cat([per_rank[0][s], per_rank[1][s]]) for s in range(4)])
     assert float((single != sharded).float().mean()) < 1e-3
+
+
+def _graph_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from onda_b200 import prototype_handler, sharding
+        from oracle import proto_oracle as po
+        case = po.synth_case(77, 6, 128, 33, 41)
+        sets = []
+        for k in range(2):
+            c = po.synth_case(200 + k, 6, 128, 33, 41, protos=case["protos"], counter=case["counter"])
+            sets.append(tuple(t.to(dev) for t in sharding.shard_batch([c["feat"], c["prior"], c["out"]], world, rank)))
+        results = []
+        for use_graph in (False, True):
+            h = prototype_handler(ma_lambda=0.9, tau=1, thresh=0.3, distance_metric="mahalanobis",
+                                  process_group=dist.group.WORLD, allreduce="oneshot")
+            h.prototypes, h.squared_mean, h.counter = (case[k].clone().to(dev) for k in ("protos", "sq_mean", "counter"))
+
+            def step(k):
+                feat, prior, out = sets[k]
+                h.pseudo_labels_fused(feat, prior, out)
+                h.ma(feat, out)
+            step(0), step(1)                                  # 2 eager steps (buffers, symmetric memory)
+            if use_graph:
+                graphs = []
+                for k in range(2):                            # capture also runs nothing: 2 + 6 replayed steps
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        step(k)
+                    graphs.append(g)
+                dist.barrier()
+                for i in range(6):
+                    graphs[i % 2].replay()
+            else:
+                for i in range(6):
+                    step(i % 2)
+            torch.cuda.synchronize()
+            dist.barrier()
+            results.append((h.prototypes.cpu().clone(), h.squared_mean.cpu().clone()))
+        ret[rank] = results
+    finally:
+        dist.destroy_process_group()
+
+
+def test_graph_replayed_steps_equal_eager_steps():
+    """The exchange fused into ma() keeps its epoch in device memory: captured once per slot, a step can be replayed from
+    a CUDA graph.  Eight steps (two eager + six replayed) give bit-identical prototypes to eight eager steps, on every rank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_graph_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        (pe, se), (pg, sg) = ret[r]
+        assert torch.equal(pe, pg) and torch.equal(se, sg)
+    assert torch.equal(ret[0][1][0], ret[1][1][0])
