@@ -10,22 +10,29 @@
 // 32 channels; a tile of 128 pixels is D/32 consecutive chunks):
 //   warps  0-15  workers, four groups of four; warp w%4 is the pixel quarter (the only TMEM lanes a warp
 //                may touch are 32*(w%4)..+31), w/4 the group; group g takes chunks g, g+4, g+8, ...
-//                Per chunk: (1) lane = pixel: coalesced 4-byte loads along the NCHW channel planes;
-//                (2) raw values -> the group's shared-memory tile [pixel][channel]; (3) centred values,
-//                split into TF32 hi/lo -> TMEM (tcgen05.st) as the A operand (lane = pixel, column =
-//                channel) and sum_j w_j x'_j^2 on the CUDA cores; (4) class sums of the chunk: lane =
-//                channel, each of the group's four warps walks its quarter of the class-sorted pixels
-//                (cut at class boundaries) and updates every class's shared-memory accumulators once.
-//                A class/channel pair has exactly one owner per tile and the group re-synchronises per
-//                chunk: fixed summation order, no atomics.
-//   warps 16-19  epilogue: tcgen05.ld of the 32 accumulator columns of their pixel, then the common
-//                per-pixel tail (epilogue.cuh): sqrt, softmax, prior rectification, label, statistics.
+//                Per chunk: (1) lane = pixel: coalesced 4-byte loads along the NCHW channel planes (the planes
+//                are only 4-byte aligned: no TMA), issued eight at a time between the phases below so that
+//                the warp never sits blocked behind the SM's miss queue; (2) raw values -> the group's
+//                shared-memory tile [pixel][channel]; (3) centred values, split into TF32 hi/lo with packed
+//                f32x2 math -> TMEM (tcgen05.st) as the A operand (lane = pixel, column = channel), and
+//                sum_j w_j x'_j^2 -> a spare TMEM column of the same lane; (4) class sums of the chunk:
+//                lane = channel, each of the group's four warps walks 32 entries of the class-sorted pixel
+//                list and adds every segment's (sum, sum of squares) to that class's shared-memory
+//                accumulators; a range that starts inside a class parks that first segment in a spare row
+//                which the warp that started the class adds after the group's barrier.  One writer per
+//                accumulator at a time, fixed summation order, no atomics.
+//   warps 16-19  epilogue: tcgen05.ld of the 32 accumulator columns and the partial columns of their pixel,
+//                then the common per-pixel tail (epilogue.cuh): sqrt, softmax, prior rectification, label,
+//                statistics.
 //   warps 20-21  sorter: per tile, class of every pixel (first argmax of the EMA logits) and a stable
 //                counting sort of the 128 pixels by class, published for the workers (double-buffered).
 //   warp   22    MMA issuer: per chunk 4 K-steps x 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
-//                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory.
+//                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory (one bulk
+//                asynchronous copy in the prologue).
 // Every mbarrier has one producer side and one consumer side that visit it phase by phase, in order.
 // Two accumulator buffers of 32 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
+// Shared memory is kept under 195 KB on purpose (tc_smem): the next carve-out step leaves 28 KB of L1 and
+// costs a quarter of the speed.
 #include <utility>
 #include "epilogue.cuh"
 

@@ -129,3 +129,19 @@ def test_oracle_step_log_stats_small_case():
     out[0, 2, 1, 1] = 1      # pixel 3 -> class 2 (agrees)
     got = po.step_log_stats(labels, out, torch.tensor([[1.0, 2.0], [3.0, 4.0]]))
     assert got == {"pseudolabel_pixel_num": 3.0, "output & prototype agreement": 0.5, "mean_prototype_intensity_values": 7.5}
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU and prints one JSON line
+    with the keys of the bench contract."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "px/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and line["vs_baseline"] is None
