@@ -213,9 +213,10 @@ class prototype_handler:
         soft = torch.empty((N, C), dtype=torch.float32, device=device) if want_soft else None
         dist = torch.empty((N, C), dtype=torch.float32, device=device) if want_dist else None
         n_sums = self._lib.onda_sums_floats(C, D)
+        sums = None
         if self.process_group is not None and self.allreduce == "oneshot" and logits3 is not None:
             sums = self._symm_slot(n_sums, device)      # written straight into peer-visible memory: no staging copy
-        else:
+        if sums is None:
             sums = torch.empty((n_sums,), dtype=torch.float32, device=device)
         impl = nat.IMPL[self.impl]
         wbytes = self._lib.onda_fused_workspace_bytes(B, D, HW, C, impl)
@@ -491,7 +492,13 @@ class prototype_handler:
     def _symm_slot(self, n, device):
         """The peer-visible input slot of the next one-shot all-reduce (two slots, alternating per call)."""
         if self._symm is None or self._symm[2] != n:
-            self._symm_init(n, device)
+            try:
+                self._symm_init(n, device)
+            except Exception as exc:      # no peer-mapped memory on this system (every rank fails alike): use NCCL
+                import warnings
+                warnings.warn(f"onda_b200: symmetric memory unavailable ({exc!r}); all-reducing with NCCL instead")
+                self.allreduce, self._symm = "nccl", None
+                return None
         return self._symm[4][self._ar_calls & 1][0]
 
     def _oneshot_args(self, sums, fused=False):
@@ -499,6 +506,8 @@ class prototype_handler:
         (rank, world, peer slot pointers, peer flag pointers, epoch) of the exchange; for the exchange fused into
         ``ma`` the last item is the device pointer of the slot's epoch counter instead."""
         slot_view = self._symm_slot(sums.numel(), sums.device)
+        if slot_view is None:
+            return None
         _, _, _, _, slots, rank, world = self._symm
         slot = self._ar_calls & 1
         _, bufs, flags, flags_fused = slots[slot]
@@ -511,7 +520,11 @@ class prototype_handler:
 
     def _allreduce_oneshot(self, sums):
         """Sum over the ranks with onda_allreduce_oneshot: inputs in symmetric (peer-mapped) memory, two slots."""
-        rank, world, bufs, flags, epoch = self._oneshot_args(sums)
+        args = self._oneshot_args(sums)
+        if args is None:                  # fell back to NCCL
+            sharding.allreduce_sums(sums, self.process_group)
+            return sums
+        rank, world, bufs, flags, epoch = args
         n = sums.numel()
         out = torch.empty((n,), dtype=torch.float32, device=sums.device)
         nat.check(self._lib.onda_allreduce_oneshot(nat.ptr(out), n, rank, world, bufs, flags, epoch,
@@ -537,9 +550,11 @@ class prototype_handler:
         cnt = self.counter if isinstance(self.counter, torch.Tensor) else None
         fused_exchange = (self.process_group is not None and self.allreduce == "oneshot" and sums.is_cuda
                           and not (need_stats and cnt is None))
+        args = self._oneshot_args(sums, fused=True) if fused_exchange else None
+        fused_exchange = args is not None
         if fused_exchange:
             # all-reduce + blend + next distance table in ONE launch: the kernel reads the peers' slots over NVLink
-            rank, world, bufs, flags, epoch_ctr = self._oneshot_args(sums, fused=True)
+            rank, world, bufs, flags, epoch_ctr = args
             reduced = self._buf(("reduced", self._ar_calls & 1), (sums.numel(),), torch.float32, device)
             table = self._buf(("table", metric), (self._lib.onda_table_floats(C, D),), torch.float32, device, zero=True)
             nat.check(self._lib.onda_ema_update_and_table_allreduce(
