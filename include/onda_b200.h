@@ -161,6 +161,23 @@ int onda_prior_mix_stats(const float* logits0, const float* logits1, const float
 size_t onda_step_log_workspace_bytes(void);
 int onda_step_log_stats(const int64_t* labels, const float* student_logits, const float* prototypes, int B, int C, int HW,
                         int D, float* out4, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- model-weight EMA ("next" row f2 of the scope table) --------------------------------------------------
+ * update_ema (framework/domain_adaptation/methods/prototypes.py:407-416) walks every parameter in a Python loop with
+ * two clones and three kernels each, then copies every buffer.  Here: ONE launch over a table of chunks that the
+ * host builds once per model pair.  mode 0: dst[i] = dst[i]*keep + src[i]*take over `count` floats (both products
+ * rounded, then the sum: bit-identical to `param_k.clone()*a + param_q.clone()*(1-a)` with keep = (float)a,
+ * take = (float)(1.0 - a)); mode 1: copy `count` bytes (buffers of any dtype, ":414-416").  A chunk is at most
+ * ONDA_EMA_CHUNK_BYTES long. */
+#define ONDA_EMA_CHUNK_BYTES 32768
+typedef struct {
+    const void* src; /* the trained model's tensor (chunk start) */
+    void* dst;       /* the EMA model's tensor (chunk start), updated in place */
+    uint32_t count;  /* floats (mode 0) or bytes (mode 1) */
+    uint32_t mode;
+} onda_ema_chunk;
+int onda_weight_ema_update(const onda_ema_chunk* chunks_device, int n_chunks, float keep, float take, void* stream);
+
 size_t onda_prior_workspace_bytes(int B, int C, int HW);
 
 /* ---- multi-GPU ---------------------------------------------------------------- */

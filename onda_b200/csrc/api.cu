@@ -475,6 +475,59 @@ __global__ void __launch_bounds__(kPriorThreads) step_log_kernel(const long long
     }
 }
 
+
+// ---- model-weight EMA (prototypes.py:407-416) as one multi-tensor launch --------------------------------
+// The host cuts every parameter / buffer into chunks of at most kEmaChunkBytes and uploads the table once; a CTA
+// walks chunks grid-stride.  mode 0: dst = dst*keep + src*take on floats, two roundings then the add exactly like
+// `param_k.clone() * a + param_q.clone() * (1 - a)`; mode 1: byte copy (buffers, any dtype).
+constexpr int kEmaThreads = 256;
+__global__ void __launch_bounds__(kEmaThreads) weight_ema_kernel(const onda_ema_chunk* __restrict__ chunks, int n_chunks,
+                                                                 float keep, float take) {
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const onda_ema_chunk ch = chunks[c];
+        const uintptr_t sa = (uintptr_t)ch.src, da = (uintptr_t)ch.dst;
+        if (ch.mode == 0) {
+            const float* s = (const float*)ch.src;
+            float* d = (float*)ch.dst;
+            const unsigned n = ch.count;
+            if (((sa | da) & 15) == 0) {
+                const unsigned n4 = n >> 2;
+                const float4* s4 = (const float4*)s;
+                float4* d4 = (float4*)d;
+                for (unsigned i = threadIdx.x; i < n4; i += kEmaThreads) {
+                    const float4 q = __ldcs(s4 + i);
+                    float4 k = d4[i];
+                    k.x = __fadd_rn(__fmul_rn(k.x, keep), __fmul_rn(q.x, take));
+                    k.y = __fadd_rn(__fmul_rn(k.y, keep), __fmul_rn(q.y, take));
+                    k.z = __fadd_rn(__fmul_rn(k.z, keep), __fmul_rn(q.z, take));
+                    k.w = __fadd_rn(__fmul_rn(k.w, keep), __fmul_rn(q.w, take));
+                    d4[i] = k;
+                }
+                for (unsigned i = (n4 << 2) + threadIdx.x; i < n; i += kEmaThreads)
+                    d[i] = __fadd_rn(__fmul_rn(d[i], keep), __fmul_rn(s[i], take));
+            } else {
+                for (unsigned i = threadIdx.x; i < n; i += kEmaThreads)
+                    d[i] = __fadd_rn(__fmul_rn(d[i], keep), __fmul_rn(s[i], take));
+            }
+        } else {
+            const unsigned n = ch.count;
+            if (((sa | da) & 15) == 0) {
+                const unsigned n16 = n >> 4;
+                const uint4* s16 = (const uint4*)ch.src;
+                uint4* d16 = (uint4*)ch.dst;
+                for (unsigned i = threadIdx.x; i < n16; i += kEmaThreads) d16[i] = s16[i];
+                const unsigned char* sb = (const unsigned char*)ch.src;
+                unsigned char* db = (unsigned char*)ch.dst;
+                for (unsigned i = (n16 << 4) + threadIdx.x; i < n; i += kEmaThreads) db[i] = sb[i];
+            } else {
+                const unsigned char* sb = (const unsigned char*)ch.src;
+                unsigned char* db = (unsigned char*)ch.dst;
+                for (unsigned i = threadIdx.x; i < n; i += kEmaThreads) db[i] = sb[i];
+            }
+        }
+    }
+}
+
 }  // namespace onda
 
 namespace onda {
@@ -770,6 +823,17 @@ int onda_step_log_stats(const int64_t* labels, const float* student_logits, cons
     else
         step_log_kernel<32><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>((const long long*)labels, student_logits, prototypes, B, C,
                                                                               HW, C * D, partials, ticket, out4);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int onda_weight_ema_update(const onda_ema_chunk* chunks_device, int n_chunks, float keep, float take, void* stream) {
+    ONDA_REQUIRE(n_chunks >= 0 && (n_chunks == 0 || chunks_device), "onda_weight_ema_update: bad chunk table");
+    if (n_chunks == 0) return ONDA_OK;
+    const int sms = cached_sm_count();
+    const int grid = n_chunks < 8 * sms ? n_chunks : 8 * sms;
+    weight_ema_kernel<<<grid, kEmaThreads, 0, (cudaStream_t)stream>>>(chunks_device, n_chunks, keep, take);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;

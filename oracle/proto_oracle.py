@@ -452,6 +452,14 @@ def step_log_stats(pseudolabels: torch.Tensor, student_out: torch.Tensor, protos
     }
 
 
+def update_ema(params_q, params_k, buffers_q, buffers_k, ema_update: float):
+    """The model-weight EMA, as written in framework/domain_adaptation/methods/prototypes.py:407-416; returns the new
+    (parameter list, buffer list) of the EMA model."""
+    new_params = [k.clone() * ema_update + q.clone() * (1.0 - ema_update) for q, k in zip(params_q, params_k)]
+    new_buffers = [q.clone() for q, _ in zip(buffers_q, buffers_k)]
+    return new_params, new_buffers
+
+
 def synth_case(seed: int, b: int, d: int, h: int, w: int, c: int = 19, protos=None,
                counter=None, sharp: float = 4.0):
     """Cityscapes-shaped synthetic inputs: blocky label map, class-separable

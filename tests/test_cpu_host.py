@@ -145,3 +145,11 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["vs_baseline"] is None
+
+
+def test_oracle_update_ema_small_case():
+    """The restated weight EMA (prototypes.py:407-416): parameters blended, buffers copied."""
+    from oracle import proto_oracle as po
+    new_p, new_b = po.update_ema([torch.tensor([2.0, 4.0])], [torch.tensor([0.0, 8.0])],
+                                 [torch.tensor([7])], [torch.tensor([1])], 0.75)
+    assert new_p[0].tolist() == [0.5, 7.0] and new_b[0].tolist() == [7]

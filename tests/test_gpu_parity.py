@@ -496,3 +496,54 @@ def test_step_log_stats_match_reference_expressions():
     assert 0 < got["pseudolabel_pixel_num"] < labels.numel() and torch.equal(labels.cpu(), ref_labels)
     with pytest.raises(ValueError):
         hd.step_log_stats(labels[:5], student.to(dev()))
+
+
+def test_weight_ema_is_bit_identical_to_the_reference_expression():
+    """update_ema (prototypes.py:407-416) as one launch: parameters of awkward sizes and alignments, int64 / bool / empty
+    buffers; bit-exact against `k.clone()*a + q.clone()*(1-a)` evaluated by torch on the CPU; three consecutive updates."""
+    from onda_b200 import WeightEma, update_ema
+    g = torch.Generator().manual_seed(5)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            big = torch.randn(70001 + 3, generator=g)
+            self.w_big = torch.nn.Parameter(big[3:])                        # 4-byte aligned only, several chunks + tail
+            self.w_mid = torch.nn.Parameter(torch.randn(8192 * 3, generator=g))   # exactly three chunks
+            self.w_small = torch.nn.Parameter(torch.randn(7, generator=g))
+            self.w_one = torch.nn.Parameter(torch.randn(1, generator=g))
+            self.bn = torch.nn.BatchNorm2d(5)                               # float buffers + int64 num_batches_tracked
+            self.register_buffer("flags", torch.tensor([True, False, True]))
+            self.register_buffer("odd_bytes", torch.arange(37, dtype=torch.uint8))
+            self.register_buffer("empty", torch.zeros(0))
+
+    q, k = Net(), Net()
+    with torch.no_grad():
+        for p in list(q.parameters()) + list(k.parameters()):
+            p.copy_(torch.randn(p.shape, generator=g) * 3)
+        q.bn.running_mean.copy_(torch.randn(5, generator=g))
+        q.bn.num_batches_tracked.fill_(12345678901)
+    pq = [p.data.clone() for p in q.parameters()]
+    pk = [p.data.clone() for p in k.parameters()]
+    bq = [b.data.clone() for b in q.buffers()]
+    bk = [b.data.clone() for b in k.buffers()]
+    q, k = q.to(dev()), k.to(dev())
+    # keep the misalignment of w_big on the device too
+    for net in (q, k):
+        padded = torch.empty(70001 + 3, device=dev())
+        padded[3:].copy_(net.w_big.data)
+        net.w_big.data = padded[3:]
+    plan = WeightEma(q, k)
+    assert plan.n_chunks >= 9 + 3 + 2
+    for a in (0.999, 0.5, 0.9995):
+        pk, bk = po.update_ema(pq, pk, bq, bk, a)
+        plan.update(a)
+    for got, want in zip(list(k.parameters()) + list(k.buffers()), pk + bk):
+        assert got.dtype == want.dtype and torch.equal(got.data.cpu(), want)
+    for got, want in zip(q.parameters(), pq):                                # the trained model is untouched
+        assert torch.equal(got.data.cpu(), want)
+    update_ema(q, k, 0.25)                                                   # functional form: builds and caches its own plan
+    pk, bk = po.update_ema(pq, pk, bq, bk, 0.25)
+    assert all(torch.equal(got.data.cpu(), want) for got, want in zip(k.parameters(), pk))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        WeightEma(Net(), Net())
