@@ -178,6 +178,16 @@ typedef struct {
 } onda_ema_chunk;
 int onda_weight_ema_update(const onda_ema_chunk* chunks_device, int n_chunks, float keep, float take, void* stream);
 
+/* ---- evaluation ("next" row f3) ---------------------------------------------------------------------------------
+ * da_model.evaluate (framework/domain_adaptation/methods/adaptation_model.py:143-160): interp(pred) (bilinear,
+ * align_corners=True, ":94-98") -> softmax -> per-image argmax -> .cpu().numpy() -> fast_hist (framework/utils/func.py:
+ * 77-79).  One launch instead: logits [B, C, h, w] at network resolution, labels [B, H, W] int64 at full resolution
+ * (entries outside [0, C) are ignored like fast_hist's mask); hist [C*C] uint64 (row = label, column = prediction) is
+ * ACCUMULATED (zero it before the first batch); pred_out [B*H*W] uint8 (nullable) receives the per-pixel prediction.
+ * The prediction is the first argmax of the interpolated logits (softmax is monotone per pixel). */
+int onda_confusion_update(const float* logits, int B, int C, int h, int w, const int64_t* labels, int H, int W,
+                          unsigned long long* hist, unsigned char* pred_out, void* stream);
+
 size_t onda_prior_workspace_bytes(int B, int C, int HW);
 
 /* ---- multi-GPU ---------------------------------------------------------------- */

@@ -7,6 +7,7 @@ Public surface (mirrors the reference's names):
 * ``onda_b200.methods`` -- ``prototype_predictions`` for the base / h-switch / v-switch / hybrid
   method classes, to be bound onto the reference's ``online_proDA`` subclasses
 * ``update_ema`` / ``WeightEma`` -- the model-weight EMA of ``online_proDA.update_ema`` as one launch
+* ``ConfusionMeter`` -- upsample + argmax + confusion matrix of ``da_model.evaluate`` in one kernel
 
 Importing the package loads ``libonda_b200.so`` lazily (on first handler construction); if the
 library has not been built the constructor raises -- there is no CPU or PyTorch fallback.
@@ -14,5 +15,6 @@ library has not been built the constructor raises -- there is no CPU or PyTorch 
 from .switching import Monitor, HybridSelect, DevSelect, static_share  # noqa: F401
 from .handler import prototype_handler  # noqa: F401
 from .ema import update_ema, WeightEma  # noqa: F401
+from .evaluation import ConfusionMeter  # noqa: F401
 
-__all__ = ["prototype_handler", "Monitor", "HybridSelect", "DevSelect", "static_share", "update_ema", "WeightEma"]
+__all__ = ["prototype_handler", "Monitor", "HybridSelect", "DevSelect", "static_share", "update_ema", "WeightEma", "ConfusionMeter"]

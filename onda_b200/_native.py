@@ -48,6 +48,7 @@ _SIGNATURES = {
     "onda_step_log_workspace_bytes": (C.c_size_t, []),
     "onda_step_log_stats": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, C.c_size_t, _p]),
     "onda_weight_ema_update": (C.c_int, [_p, C.c_int, C.c_float, C.c_float, _p]),
+    "onda_confusion_update": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p]),
     "onda_allreduce_oneshot": (C.c_int, [_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(_p), C.POINTER(_p),
                                          C.c_uint32, _p]),
     "onda_ema_update_and_table_allreduce": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_float, C.c_int, _p,

@@ -528,6 +528,57 @@ __global__ void __launch_bounds__(kEmaThreads) weight_ema_kernel(const onda_ema_
     }
 }
 
+
+// ---- evaluation: upsample + argmax + confusion matrix in one pass (adaptation_model.py:143-160) ------------------
+// The reference materialises interp(pred) at full resolution (19 x 1024 x 2048 floats per image), softmaxes it, takes the
+// argmax, copies it to the host and bincounts there.  Here one thread per full-resolution pixel interpolates the 19
+// low-resolution logits bilinearly (align_corners=True, torch's index/weight arithmetic), takes the first argmax
+// (softmax is monotone per pixel, so the argmax is that of the interpolated logits) and counts (label, prediction) in a
+// shared-memory histogram; integer atomics only, so the result does not depend on scheduling.
+constexpr int kConfThreads = 256;
+template <int CP>
+__global__ void __launch_bounds__(kConfThreads) confusion_kernel(const float* __restrict__ logits, int B, int C, int h, int w,
+                                                                 const long long* __restrict__ labels, int H, int W,
+                                                                 unsigned long long* __restrict__ hist,
+                                                                 unsigned char* __restrict__ pred_out) {
+    __shared__ unsigned int sh[ONDA_MAX_CLASSES * ONDA_MAX_CLASSES];
+    for (int i = threadIdx.x; i < C * C; i += kConfThreads) sh[i] = 0u;
+    __syncthreads();
+    const float scale_h = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;      // area_pixel_compute_scale, align_corners
+    const float scale_w = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const long long HWo = (long long)H * W, N = (long long)B * HWo;
+    const long long hw = (long long)h * w;
+    for (long long n = (long long)blockIdx.x * kConfThreads + threadIdx.x; n < N; n += (long long)gridDim.x * kConfThreads) {
+        const long long b = n / HWo, r = n - b * HWo;
+        const int y = (int)(r / W), x = (int)(r - (long long)y * W);
+        const float h1r = __fmul_rn(scale_h, (float)y), w1r = __fmul_rn(scale_w, (float)x);
+        const int h1 = (int)h1r, w1 = (int)w1r;
+        const int h1p = h1 < h - 1 ? 1 : 0, w1p = w1 < w - 1 ? 1 : 0;
+        const float h1l = __fsub_rn(h1r, (float)h1), h0l = __fsub_rn(1.f, h1l);
+        const float w1l = __fsub_rn(w1r, (float)w1), w0l = __fsub_rn(1.f, w1l);
+        const float* base = logits + (b * C) * hw + (long long)h1 * w + w1;
+        float best = 0.f;
+        int arg = 0;
+#pragma unroll
+        for (int k = 0; k < CP; ++k) {
+            if (k < C) {
+                const float* p = base + (long long)k * hw;
+                const float v00 = __ldg(p), v01 = __ldg(p + w1p), v10 = __ldg(p + h1p * w), v11 = __ldg(p + h1p * w + w1p);
+                const float top = __fadd_rn(__fmul_rn(w0l, v00), __fmul_rn(w1l, v01));
+                const float bot = __fadd_rn(__fmul_rn(w0l, v10), __fmul_rn(w1l, v11));
+                const float v = __fadd_rn(__fmul_rn(h0l, top), __fmul_rn(h1l, bot));
+                if (k == 0 || torch_greater(v, best)) { best = v; arg = k; }
+            }
+        }
+        if (pred_out != nullptr) pred_out[n] = (unsigned char)arg;
+        const long long lab = labels[n];
+        if (lab >= 0 && lab < C) atomicAdd(&sh[(int)lab * C + arg], 1u);          // fast_hist: func.py:77-79
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * C; i += kConfThreads)
+        if (sh[i] != 0u) atomicAdd(hist + i, (unsigned long long)sh[i]);
+}
+
 }  // namespace onda
 
 namespace onda {
@@ -834,6 +885,24 @@ int onda_weight_ema_update(const onda_ema_chunk* chunks_device, int n_chunks, fl
     const int sms = cached_sm_count();
     const int grid = n_chunks < 8 * sms ? n_chunks : 8 * sms;
     weight_ema_kernel<<<grid, kEmaThreads, 0, (cudaStream_t)stream>>>(chunks_device, n_chunks, keep, take);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
+int onda_confusion_update(const float* logits, int B, int C, int h, int w, const int64_t* labels, int H, int W,
+                          unsigned long long* hist, unsigned char* pred_out, void* stream) {
+    ONDA_REQUIRE(logits && labels && hist, "onda_confusion_update: null pointer");
+    ONDA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0 && C <= ONDA_MAX_CLASSES,
+                 "onda_confusion_update: bad shape B=%d C=%d %dx%d -> %dx%d", B, C, h, w, H, W);
+    const long long N = (long long)B * H * W;
+    const int sms = cached_sm_count();
+    long long want = (N + kConfThreads - 1) / kConfThreads;
+    const int grid = (int)(want < 8LL * sms ? want : 8LL * sms);
+    if (padded_classes(C) == 20)
+        confusion_kernel<20><<<grid, kConfThreads, 0, (cudaStream_t)stream>>>(logits, B, C, h, w, (const long long*)labels, H, W, hist, pred_out);
+    else
+        confusion_kernel<32><<<grid, kConfThreads, 0, (cudaStream_t)stream>>>(logits, B, C, h, w, (const long long*)labels, H, W, hist, pred_out);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;

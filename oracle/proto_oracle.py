@@ -460,6 +460,24 @@ def update_ema(params_q, params_k, buffers_q, buffers_k, ema_update: float):
     return new_params, new_buffers
 
 
+def eval_confusion(pred: torch.Tensor, labels: torch.Tensor, n: int, size):
+    """Prediction map and confusion counts of one batch, as written in
+    framework/domain_adaptation/methods/adaptation_model.py:94-98,143-160 and framework/utils/func.py:77-79.
+    Returns (softmaxed upsampled prediction (B, n, H, W), per-pixel argmax (B, H, W) int64, hist (n, n) int64)."""
+    import numpy as np
+    interp = torch.nn.Upsample(size=size, mode="bilinear", align_corners=True)
+    prob = interp(pred).softmax(axis=1)
+    hist = np.zeros((n, n), dtype=np.int64)
+    preds = []
+    for item_pred, label in zip(prob, labels):
+        a = label.numpy().flatten()
+        b = item_pred.permute(1, 2, 0).argmax(dim=2).cpu().numpy().flatten()
+        k = (a >= 0) & (a < n)
+        hist += np.bincount(n * a[k].astype(int) + b[k], minlength=n ** 2).reshape(n, n)
+        preds.append(torch.from_numpy(b.reshape(label.shape)))
+    return prob, torch.stack(preds), hist
+
+
 def synth_case(seed: int, b: int, d: int, h: int, w: int, c: int = 19, protos=None,
                counter=None, sharp: float = 4.0):
     """Cityscapes-shaped synthetic inputs: blocky label map, class-separable

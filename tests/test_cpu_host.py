@@ -153,3 +153,17 @@ def test_oracle_update_ema_small_case():
     new_p, new_b = po.update_ema([torch.tensor([2.0, 4.0])], [torch.tensor([0.0, 8.0])],
                                  [torch.tensor([7])], [torch.tensor([1])], 0.75)
     assert new_p[0].tolist() == [0.5, 7.0] and new_b[0].tolist() == [7]
+
+
+def test_oracle_eval_confusion_small_case():
+    """The restated evaluation counters (adaptation_model.py:143-160, func.py:77-79) on a hand-checkable case."""
+    from oracle import proto_oracle as po
+    pred = torch.zeros(1, 3, 2, 2)
+    pred[0, 1, 0, 0] = 5     # top-left -> class 1
+    pred[0, 2, 0, 1] = 5     # top-right -> class 2
+    pred[0, 0, 1, 0] = 5     # bottom-left -> class 0
+    pred[0, 2, 1, 1] = 5     # bottom-right -> class 2
+    labels = torch.tensor([[[1, 2], [255, 0]]])
+    _, p, hist = po.eval_confusion(pred, labels, 3, (2, 2))
+    assert p.tolist() == [[[1, 2], [0, 2]]]
+    assert hist.tolist() == [[0, 0, 1], [0, 1, 0], [0, 0, 1]]     # (label 0 -> pred 2), (1 -> 1), (2 -> 2); 255 ignored

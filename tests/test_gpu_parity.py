@@ -547,3 +547,45 @@ def test_weight_ema_is_bit_identical_to_the_reference_expression():
     assert all(torch.equal(got.data.cpu(), want) for got, want in zip(k.parameters(), pk))
     with pytest.raises(RuntimeError, match="CUDA"):
         WeightEma(Net(), Net())
+
+
+@pytest.mark.parametrize("h,w,H,W", [(9, 17, 65, 129), (10, 13, 37, 50), (33, 65, 257, 513), (6, 7, 6, 7)])
+def test_confusion_meter_matches_reference_evaluation(h, w, H, W):
+    """da_model.evaluate's counters (adaptation_model.py:143-160, func.py:77-79) from one fused kernel.  The per-pixel
+    prediction equals the reference's argmax of softmax(interp(pred)) except where that softmax's top-2 margin is below
+    1e-6 (interpolation rounding); the matrix is exactly fast_hist of our own prediction, and equal to the reference's
+    when no exempt pixel flipped.  Labels carry 255 and -1 (ignored)."""
+    import numpy as np
+    from onda_b200 import ConfusionMeter
+    g = torch.Generator().manual_seed(1000 + h * w)
+    B, C = 3, 19
+    meter = ConfusionMeter(C, dev())
+    total_ref = np.zeros((C, C), dtype=np.int64)
+    for batch in range(2):
+        pred = torch.randn(B, C, h, w, generator=g) * 3
+        pred[0, 4] = pred[0, 3]                                   # exact ties between two classes: first index wins
+        labels = torch.randint(0, C, (B, H, W), generator=g)
+        labels[torch.rand(B, H, W, generator=g) < 0.1] = 255
+        labels[torch.rand(B, H, W, generator=g) < 0.02] = -1
+        prob, ref_pred, ref_hist = po.eval_confusion(pred, labels, C, (H, W))
+        before = meter.hist().copy()
+        got = meter.update(pred.to(dev()), labels if batch == 0 else labels.to(dev()), return_prediction=True).cpu().long()
+        top2 = prob.topk(2, dim=1)[0]
+        exempt = (top2[:, 0] - top2[:, 1]) < 1e-6
+        assert int(((got != ref_pred) & ~exempt).sum()) == 0
+        a, b_ = labels.numpy().flatten(), got.numpy().flatten()
+        k = (a >= 0) & (a < C)
+        own = np.bincount(C * a[k] + b_[k], minlength=C * C).reshape(C, C)
+        assert np.array_equal(meter.hist() - before, own)          # exact counting, accumulated over batches
+        if int((got != ref_pred).sum()) == 0:
+            assert np.array_equal(own, ref_hist)
+        total_ref += ref_hist
+    if np.array_equal(meter.hist(), total_ref):
+        iu_ref = np.diag(total_ref) / (total_ref.sum(1) + total_ref.sum(0) - np.diag(total_ref) + np.finfo(float).eps)
+        assert np.array_equal(meter.per_class_iu(), iu_ref)
+    meter.reset()
+    assert meter.hist().sum() == 0
+    with pytest.raises(ValueError):
+        meter.update(torch.zeros(1, 5, 4, 4, device=dev()), torch.zeros(1, 8, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        meter.update(torch.zeros(1, C, 4, 4), torch.zeros(1, 8, 8))
