@@ -531,11 +531,14 @@ __global__ void __launch_bounds__(kEmaThreads) weight_ema_kernel(const onda_ema_
 
 // ---- evaluation: upsample + argmax + confusion matrix in one pass (adaptation_model.py:143-160) ------------------
 // The reference materialises interp(pred) at full resolution (19 x 1024 x 2048 floats per image), softmaxes it, takes the
-// argmax, copies it to the host and bincounts there.  Here one thread per full-resolution pixel interpolates the 19
-// low-resolution logits bilinearly (align_corners=True, torch's index/weight arithmetic), takes the first argmax
-// (softmax is monotone per pixel, so the argmax is that of the interpolated logits) and counts (label, prediction) in a
-// shared-memory histogram; integer atomics only, so the result does not depend on scheduling.
+// argmax, copies it to the host and bincounts there.  Here a thread owns one full-resolution column of a strip of rows:
+// it keeps, per class, the two source rows of the bilinear interpolation already interpolated along x (align_corners=
+// True, torch's index/weight arithmetic) in registers, so walking down the strip costs two multiplies and an add per
+// class and pixel and new loads only when the source row changes (every ~8 pixels).  First argmax (softmax is monotone
+// per pixel, so the argmax is that of the interpolated logits), then (label, prediction) is counted in a shared-memory
+// histogram; integer atomics only, so the result does not depend on scheduling.  The upsampled tensor never exists.
 constexpr int kConfThreads = 256;
+constexpr int kConfStrip = 32;
 template <int CP>
 __global__ void __launch_bounds__(kConfThreads) confusion_kernel(const float* __restrict__ logits, int B, int C, int h, int w,
                                                                  const long long* __restrict__ labels, int H, int W,
@@ -546,33 +549,69 @@ __global__ void __launch_bounds__(kConfThreads) confusion_kernel(const float* __
     __syncthreads();
     const float scale_h = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;      // area_pixel_compute_scale, align_corners
     const float scale_w = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-    const long long HWo = (long long)H * W, N = (long long)B * HWo;
     const long long hw = (long long)h * w;
-    for (long long n = (long long)blockIdx.x * kConfThreads + threadIdx.x; n < N; n += (long long)gridDim.x * kConfThreads) {
-        const long long b = n / HWo, r = n - b * HWo;
-        const int y = (int)(r / W), x = (int)(r - (long long)y * W);
-        const float h1r = __fmul_rn(scale_h, (float)y), w1r = __fmul_rn(scale_w, (float)x);
-        const int h1 = (int)h1r, w1 = (int)w1r;
-        const int h1p = h1 < h - 1 ? 1 : 0, w1p = w1 < w - 1 ? 1 : 0;
-        const float h1l = __fsub_rn(h1r, (float)h1), h0l = __fsub_rn(1.f, h1l);
+    const int n_colblocks = (W + kConfThreads - 1) / kConfThreads;
+    const int n_strips = (H + kConfStrip - 1) / kConfStrip;
+    const long long items = (long long)B * n_strips * n_colblocks;
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const int cb = (int)(it % n_colblocks);
+        const long long t2 = it / n_colblocks;
+        const int strip = (int)(t2 % n_strips), b = (int)(t2 / n_strips);
+        const int x = cb * kConfThreads + threadIdx.x;
+        if (x >= W) continue;
+        const float w1r = __fmul_rn(scale_w, (float)x);
+        const int w1 = (int)w1r, w1p = w1 < w - 1 ? 1 : 0;
         const float w1l = __fsub_rn(w1r, (float)w1), w0l = __fsub_rn(1.f, w1l);
-        const float* base = logits + (b * C) * hw + (long long)h1 * w + w1;
-        float best = 0.f;
-        int arg = 0;
+        const float* img = logits + ((long long)b * C) * hw + w1;
+        float top[CP], bot[CP];              // rows rowT / rowB of every class, interpolated along x
+        int rowT = -1, rowB = -1;
+        auto load_row = [&](int r, float (&dst)[CP]) {
 #pragma unroll
-        for (int k = 0; k < CP; ++k) {
-            if (k < C) {
-                const float* p = base + (long long)k * hw;
-                const float v00 = __ldg(p), v01 = __ldg(p + w1p), v10 = __ldg(p + h1p * w), v11 = __ldg(p + h1p * w + w1p);
-                const float top = __fadd_rn(__fmul_rn(w0l, v00), __fmul_rn(w1l, v01));
-                const float bot = __fadd_rn(__fmul_rn(w0l, v10), __fmul_rn(w1l, v11));
-                const float v = __fadd_rn(__fmul_rn(h0l, top), __fmul_rn(h1l, bot));
-                if (k == 0 || torch_greater(v, best)) { best = v; arg = k; }
+            for (int k = 0; k < CP; ++k) {
+                if (k < C) {
+                    const float* p = img + (long long)k * hw + (long long)r * w;
+                    dst[k] = __fadd_rn(__fmul_rn(w0l, __ldg(p)), __fmul_rn(w1l, __ldg(p + w1p)));
+                }
             }
+        };
+        const int y_end = (strip + 1) * kConfStrip < H ? (strip + 1) * kConfStrip : H;
+        for (int y = strip * kConfStrip; y < y_end; ++y) {
+            const float h1r = __fmul_rn(scale_h, (float)y);
+            const int h1 = (int)h1r, h1p = h1 < h - 1 ? 1 : 0;
+            const float h1l = __fsub_rn(h1r, (float)h1), h0l = __fsub_rn(1.f, h1l);
+            const int rT = h1, rB = h1 + h1p;
+            if (rT != rowT) {
+                if (rT == rowB) {
+#pragma unroll
+                    for (int k = 0; k < CP; ++k) top[k] = bot[k];
+                } else {
+                    load_row(rT, top);
+                }
+                rowT = rT;
+            }
+            if (rB != rowB) {
+                if (rB == rowT) {
+#pragma unroll
+                    for (int k = 0; k < CP; ++k) bot[k] = top[k];
+                } else {
+                    load_row(rB, bot);
+                }
+                rowB = rB;
+            }
+            float best = 0.f;
+            int arg = 0;
+#pragma unroll
+            for (int k = 0; k < CP; ++k) {
+                if (k < C) {
+                    const float v = __fadd_rn(__fmul_rn(h0l, top[k]), __fmul_rn(h1l, bot[k]));
+                    if (k == 0 || torch_greater(v, best)) { best = v; arg = k; }
+                }
+            }
+            const long long n = ((long long)b * H + y) * W + x;
+            if (pred_out != nullptr) pred_out[n] = (unsigned char)arg;
+            const long long lab = labels[n];
+            if (lab >= 0 && lab < C) atomicAdd(&sh[(int)lab * C + arg], 1u);          // fast_hist: func.py:77-79
         }
-        if (pred_out != nullptr) pred_out[n] = (unsigned char)arg;
-        const long long lab = labels[n];
-        if (lab >= 0 && lab < C) atomicAdd(&sh[(int)lab * C + arg], 1u);          // fast_hist: func.py:77-79
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C * C; i += kConfThreads)
@@ -895,9 +934,8 @@ int onda_confusion_update(const float* logits, int B, int C, int h, int w, const
     ONDA_REQUIRE(logits && labels && hist, "onda_confusion_update: null pointer");
     ONDA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0 && C <= ONDA_MAX_CLASSES,
                  "onda_confusion_update: bad shape B=%d C=%d %dx%d -> %dx%d", B, C, h, w, H, W);
-    const long long N = (long long)B * H * W;
     const int sms = cached_sm_count();
-    long long want = (N + kConfThreads - 1) / kConfThreads;
+    const long long want = (long long)B * ((H + kConfStrip - 1) / kConfStrip) * ((W + kConfThreads - 1) / kConfThreads);
     const int grid = (int)(want < 8LL * sms ? want : 8LL * sms);
     if (padded_classes(C) == 20)
         confusion_kernel<20><<<grid, kConfThreads, 0, (cudaStream_t)stream>>>(logits, B, C, h, w, (const long long*)labels, H, W, hist, pred_out);
