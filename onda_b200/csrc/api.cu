@@ -538,11 +538,10 @@ __global__ void __launch_bounds__(kEmaThreads) weight_ema_kernel(const onda_ema_
 // per pixel, so the argmax is that of the interpolated logits), then (label, prediction) is counted in a shared-memory
 // histogram; integer atomics only, so the result does not depend on scheduling.  The upsampled tensor never exists.
 constexpr int kConfThreads = 256;
-constexpr int kConfStrip = 32;
 template <int CP>
 __global__ void __launch_bounds__(kConfThreads) confusion_kernel(const float* __restrict__ logits, int B, int C, int h, int w,
                                                                  const long long* __restrict__ labels, int H, int W,
-                                                                 unsigned long long* __restrict__ hist,
+                                                                 int strip_rows, unsigned long long* __restrict__ hist,
                                                                  unsigned char* __restrict__ pred_out) {
     __shared__ unsigned int sh[ONDA_MAX_CLASSES * ONDA_MAX_CLASSES];
     for (int i = threadIdx.x; i < C * C; i += kConfThreads) sh[i] = 0u;
@@ -551,7 +550,7 @@ __global__ void __launch_bounds__(kConfThreads) confusion_kernel(const float* __
     const float scale_w = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
     const long long hw = (long long)h * w;
     const int n_colblocks = (W + kConfThreads - 1) / kConfThreads;
-    const int n_strips = (H + kConfStrip - 1) / kConfStrip;
+    const int n_strips = (H + strip_rows - 1) / strip_rows;
     const long long items = (long long)B * n_strips * n_colblocks;
     for (long long it = blockIdx.x; it < items; it += gridDim.x) {
         const int cb = (int)(it % n_colblocks);
@@ -574,8 +573,8 @@ __global__ void __launch_bounds__(kConfThreads) confusion_kernel(const float* __
                 }
             }
         };
-        const int y_end = (strip + 1) * kConfStrip < H ? (strip + 1) * kConfStrip : H;
-        for (int y = strip * kConfStrip; y < y_end; ++y) {
+        const int y_end = (strip + 1) * strip_rows < H ? (strip + 1) * strip_rows : H;
+        for (int y = strip * strip_rows; y < y_end; ++y) {
             const float h1r = __fmul_rn(scale_h, (float)y);
             const int h1 = (int)h1r, h1p = h1 < h - 1 ? 1 : 0;
             const float h1l = __fsub_rn(h1r, (float)h1), h0l = __fsub_rn(1.f, h1l);
@@ -935,12 +934,19 @@ int onda_confusion_update(const float* logits, int B, int C, int h, int w, const
     ONDA_REQUIRE(B > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0 && C <= ONDA_MAX_CLASSES,
                  "onda_confusion_update: bad shape B=%d C=%d %dx%d -> %dx%d", B, C, h, w, H, W);
     const int sms = cached_sm_count();
-    const long long want = (long long)B * ((H + kConfStrip - 1) / kConfStrip) * ((W + kConfThreads - 1) / kConfThreads);
+    // rows per strip: long strips reuse the interpolated source rows longest; short ones when the image alone would
+    // not fill the machine (at least two CTAs per SM wanted)
+    int strip_rows = 32;
+    long long want = 0;
+    for (;; strip_rows >>= 1) {
+        want = (long long)B * ((H + strip_rows - 1) / strip_rows) * ((W + kConfThreads - 1) / kConfThreads);
+        if (want >= 2LL * sms || strip_rows <= 4) break;
+    }
     const int grid = (int)(want < 8LL * sms ? want : 8LL * sms);
     if (padded_classes(C) == 20)
-        confusion_kernel<20><<<grid, kConfThreads, 0, (cudaStream_t)stream>>>(logits, B, C, h, w, (const long long*)labels, H, W, hist, pred_out);
+        confusion_kernel<20><<<grid, kConfThreads, 0, (cudaStream_t)stream>>>(logits, B, C, h, w, (const long long*)labels, H, W, strip_rows, hist, pred_out);
     else
-        confusion_kernel<32><<<grid, kConfThreads, 0, (cudaStream_t)stream>>>(logits, B, C, h, w, (const long long*)labels, H, W, hist, pred_out);
+        confusion_kernel<32><<<grid, kConfThreads, 0, (cudaStream_t)stream>>>(logits, B, C, h, w, (const long long*)labels, H, W, strip_rows, hist, pred_out);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
