@@ -324,7 +324,68 @@ def stats_case():
         ref_entropy=prob_2_entropy(pa))
 
 
+def widened_case():
+    """Rows widened beyond the prototype path: the reference's own update_ema (prototypes.py:407-416) on a real
+    hybrid_proDA instance, and the inner loop of da_model.evaluate (adaptation_model.py:143-160) with the reference's
+    own ``interp`` module, ``fast_hist`` and ``per_class_iu``."""
+    import yaml
+    from framework.utils.func import fast_hist, per_class_iu
+    with open(os.path.join(REF, "configs", "hybrid_switch.yml")) as f:
+        cfg = to_attr(yaml.safe_load(f))
+    cfg.OTHERS.DEVICE = "cpu"
+    cfg.NUM_CLASSES = 19
+    cfg.OTHERS.SNAPSHOT_DIR = "/tmp/onda_golden_snap"
+    cfg.SCHEME.RESOLUTION = [56, 32]              # (W, H) of the full-resolution label maps of this fixture
+    spec = cfg.METHOD.ADAPTATION.PROTO_ONLINE_HYBRIDSWITCH
+    spec.set_ = "golden"
+    spec.LOAD_PROTO = AttrDict()
+
+    class FakeWithBuffers(FakeSegModel):
+        def __init__(self, seed=0):
+            super().__init__(seed=seed)
+            self.bn = torch.nn.BatchNorm2d(24)
+
+    model = FakeWithBuffers(seed=3)
+    method = ref_hybrid.hybrid_proDA(model, cfg, spec)
+    g = torch.Generator().manual_seed(77)
+    with torch.no_grad():                          # a trained model that has moved away from its EMA copy
+        for p in method.model.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.05)
+        method.model.bn.running_mean.add_(torch.randn(24, generator=g))
+        method.model.bn.running_var.mul_(1.3)
+        method.model.bn.num_batches_tracked.fill_(41)
+    out = {"ema_update": np.float64(spec.EMA_UPDATE)}
+    for i, (q, k) in enumerate(zip(method.model.parameters(), method.ema_model.parameters())):
+        out[f"q{i}"], out[f"k{i}_before"] = q.data.clone(), k.data.clone()
+    for i, (q, k) in enumerate(zip(method.model.buffers(), method.ema_model.buffers())):
+        out[f"bq{i}"], out[f"bk{i}_before"] = q.data.clone(), k.data.clone()
+    for step in range(3):                          # three consecutive updates
+        method.update_ema()
+    for i, k in enumerate(method.ema_model.parameters()):
+        out[f"k{i}_after3"] = k.data.clone()
+    for i, k in enumerate(method.ema_model.buffers()):
+        out[f"bk{i}_after3"] = k.data.clone()
+    out["n_params"] = np.int64(len(list(method.model.parameters())))
+    out["n_buffers"] = np.int64(len(list(method.model.buffers())))
+    # evaluation inner loop with the reference's own objects
+    pred = torch.randn(3, 19, 4, 7, generator=g) * 3
+    labels = torch.randint(0, 19, (3, 32, 56), generator=g)
+    labels[torch.rand(3, 32, 56, generator=g) < 0.1] = 255
+    prob = method.interp(pred).softmax(axis=1)
+    counter = 0
+    preds = []
+    for item_pred, label in zip(prob, labels):
+        lab = label.numpy()
+        item_pred_labels = item_pred.permute(1, 2, 0).argmax(dim=2).cpu().numpy()
+        counter = counter + fast_hist(lab.flatten(), item_pred_labels.flatten(), cfg.NUM_CLASSES)
+        preds.append(item_pred_labels)
+    out.update(eval_pred=pred, eval_labels=labels, eval_prob=prob, eval_argmax=np.stack(preds), eval_hist=counter,
+               eval_iu=per_class_iu(counter))
+    npz("widened_rows.npz", **out)
+
+
 def main():
+    widened_case()
     p_legacy, c_legacy = legacy_pickle()
     npz("prototypes_legacy.npz", protos=p_legacy, counter=c_legacy)
     ops_case("ops_euclid_small.npz", 11, 2, 48, 9, 13, "euclidean")

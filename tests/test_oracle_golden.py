@@ -138,3 +138,28 @@ def test_fp64_truth_bounds_reference_error():
     shifted = po.shift_by_row_min(truth)
     err = (shifted.float() - T(z["ref_dist"])).abs() / truth.float()
     assert err.max() < 5e-6
+
+
+def test_widened_rows_match_reference():
+    """update_ema (prototypes.py:407-416) and the evaluation inner loop (adaptation_model.py:143-160, func.py:77-85) as the
+    REAL reference computed them (tests/golden/make_golden.py::widened_case): the restatements are bit-identical."""
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN, "widened_rows.npz"))
+    n_p, n_b = int(z["n_params"]), int(z["n_buffers"])
+    pq = [torch.from_numpy(z[f"q{i}"]) for i in range(n_p)]
+    pk = [torch.from_numpy(z[f"k{i}_before"]) for i in range(n_p)]
+    bq = [torch.from_numpy(z[f"bq{i}"]) for i in range(n_b)]
+    bk = [torch.from_numpy(z[f"bk{i}_before"]) for i in range(n_b)]
+    for _ in range(3):
+        pk, bk = po.update_ema(pq, pk, bq, bk, float(z["ema_update"]))
+    for i in range(n_p):
+        assert torch.equal(pk[i], torch.from_numpy(z[f"k{i}_after3"]))
+    for i in range(n_b):
+        want = torch.from_numpy(z[f"bk{i}_after3"])
+        assert bk[i].dtype == want.dtype and torch.equal(bk[i], want)
+    pred, labels = torch.from_numpy(z["eval_pred"]), torch.from_numpy(z["eval_labels"])
+    prob, arg, hist = po.eval_confusion(pred, labels, 19, tuple(labels.shape[1:]))
+    assert torch.equal(prob, torch.from_numpy(z["eval_prob"]))
+    assert np.array_equal(arg.numpy(), z["eval_argmax"]) and np.array_equal(hist, z["eval_hist"])
+    iu = np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist) + np.finfo(float).eps)
+    assert np.array_equal(iu, z["eval_iu"])
