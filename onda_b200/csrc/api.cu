@@ -54,15 +54,20 @@ void timing_end(cudaStream_t s) {
     ++g_timed;
 }
 
-static int cached_sm_count() {
-    static int sms = 0;
-    if (sms > 0) return sms;
+int current_device() {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
+int cached_sm_count() {
+    static int sms[kMaxDevices] = {};
+    const int dev = current_device();
+    if (sms[dev] > 0) return sms[dev];
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    sms = v;
-    return sms;
+    sms[dev] = v;
+    return v;
 }
 
 // ---- distance table (optionally fused with the EMA blend) ---------------------------------------
@@ -218,10 +223,11 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
             if (k < T.CP) table[T.off_q + (size_t)j * T.CP + k] = qf;
             // TF32 split of -2*Q in the tcgen05 B-operand layout (common.cuh); classes >= C are zero rows
             const float v = -2.f * qf;
+            // (both parts rounded to nearest TF32 here: the tensor core would truncate the low 13 bits)
             const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
             const size_t bi = (size_t)(j >> 2) * 128 + (size_t)k * 4 + (j & 3);
             table[T.off_qhi + bi] = hi;
-            table[T.off_qlo + bi] = v - hi;
+            table[T.off_qlo + bi] = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bk += __shfl_xor_sync(0xffffffffu, bk, o);   // over the CTA's 32 channels
@@ -759,7 +765,7 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
     const long long n_tiles = ((long long)B * HW + kTilePixels - 1) / kTilePixels;
     const bool tc_ok = want_dist && tc_supported(B, D, HW, C);
     ONDA_REQUIRE(impl != ONDA_IMPL_TCGEN05 || tc_ok || !want_dist,
-                 "onda_pseudolabel_fused: the tcgen05 kernel covers D = 128 or 256 and C <= 32 "
+                 "onda_pseudolabel_fused: the tcgen05 kernel covers D = 64, 128, 192 or 256 and C <= 32 "
                  "(got D=%d C=%d)", D, C);
     // AUTO: tensor-core kernel when the shape allows and there are enough tiles to fill the machine
     const bool use_tc = tc_ok && (impl == ONDA_IMPL_TCGEN05 || (impl == ONDA_IMPL_AUTO && n_tiles >= 32));
@@ -784,8 +790,10 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
 
     int n_cta, n_stat;
     if (use_tc) {
-        p.nslices = 1; p.slice_channels = D;
-        n_cta = tc_grid(pl.tiles, sms);
+        p.nslices = 1; p.slice_channels = D; p.cluster = 1;
+        p.tiles_per_img = (HW + kTilePixels - 1) / kTilePixels;
+        p.tiles = tc_tiles(B, HW);
+        n_cta = tc_grid(p.tiles, sms);
         n_stat = n_cta;
         int rc = launch_fused_tc(p, n_cta, want_sums, stream);
         if (rc != ONDA_OK) return rc;

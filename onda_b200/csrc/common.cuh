@@ -16,6 +16,10 @@ void count_launch(int n);
 // optional event bracket around the dominant kernel (api.cu); both are no-ops unless timing is enabled
 void timing_begin(cudaStream_t s);
 void timing_end(cudaStream_t s);
+// per-device caches (kernel attributes, SM counts) are indexed by the current device, clamped to kMaxDevices - 1
+constexpr int kMaxDevices = 64;
+int current_device();
+int cached_sm_count();
 
 #define ONDA_CUDA_TRY(expr)                                  \
     do {                                                     \

@@ -23,7 +23,10 @@ struct FusedParams {
     float* dots_scratch;   // [nslices][CP + 1][N] partial dot products when nslices > 1
     int nslices;           // channel slices (gridDim.y)
     int slice_channels;    // channels per slice, multiple of 32
-    int tiles;             // ceil(N / 128)
+    int tiles;             // CUDA-core kernel: ceil(N / 128) tiles of the flattened pixel axis; tcgen05 kernel: B * tiles_per_img
+    int tiles_per_img;     // tcgen05 kernel: ceil(HW / 128) -- its tiles never straddle two images (bulk row copies)
+    int cluster;           // tcgen05 kernel: CTAs per cluster = channel slices of one tile (slice_channels = D / cluster)
+    int nstage;            // tcgen05 kernel: stages of the feature ring in shared memory
     long long* debug;      // optional [gridDim.x][32 warps][8] cycle counters (onda_debug_set_buffer), else null
 };
 
@@ -37,6 +40,7 @@ int launch_fused_simt(const FusedParams& p, const SimtPlan& pl, bool dist, bool 
 
 // tcgen05 kernel (fused_tc.cu)
 bool tc_supported(int B, int D, int HW, int C);
+int tc_tiles(int B, int HW);
 int tc_grid(int tiles, int sms);
 int launch_fused_tc(const FusedParams& p, int grid, bool sums, cudaStream_t stream);
 
@@ -171,12 +175,14 @@ __device__ __forceinline__ void warp_copy_rows(const float* stage_rows, float* g
 
 // Tail for one tile row handled by thread `t` (pixel n = tile_base + t).  `stage` is a
 // [128][CP+1] shared-memory slab; rows 32*warp .. 32*warp+31 belong to this warp.
+// `tile_rows` = number of valid rows of this tile (rows tile_base .. tile_base + tile_rows - 1 exist).
 template <int CP, bool WANT_DIST>
-__device__ __forceinline__ void finish_pixel(const FusedParams& p, const int C, float (&d2)[CP], long long tile_base, int t,
-                                             float* stage, PixelStats& st, const float* preloaded_prior = nullptr) {
+__device__ __forceinline__ void finish_pixel_rows(const FusedParams& p, const int C, float (&d2)[CP], long long tile_base,
+                                                  int tile_rows, int t, float* stage, PixelStats& st,
+                                                  const float* preloaded_prior = nullptr) {
     const int lane = t & 31, warp = t >> 5;
     const long long n = tile_base + t;
-    const bool valid = n < p.N;
+    const bool valid = t < tile_rows;
     const bool want_post = (p.labels != nullptr) || (p.soft != nullptr);
     float pri[CP];
     float dsh[WANT_DIST ? CP : 1];
@@ -206,8 +212,8 @@ __device__ __forceinline__ void finish_pixel(const FusedParams& p, const int C, 
         if (p.labels != nullptr) p.labels[n] = (long long)label;
     }
     const long long warp_base = tile_base + 32 * warp;
-    long long remain = p.N - warp_base;
-    const int rows = remain <= 0 ? 0 : (remain < 32 ? (int)remain : 32);
+    const int remain = tile_rows - 32 * warp;
+    const int rows = remain <= 0 ? 0 : (remain < 32 ? remain : 32);
     float* my_rows = stage + (32 * warp) * (CP + 1);
     if (p.soft != nullptr) {
         __syncwarp();
@@ -225,6 +231,15 @@ __device__ __forceinline__ void finish_pixel(const FusedParams& p, const int C, 
         __syncwarp();
         warp_copy_rows<CP>(my_rows, p.dist + warp_base * C, rows, C, lane);
     }
+}
+
+// Tile of the flattened pixel axis: rows beyond N do not exist.
+template <int CP, bool WANT_DIST>
+__device__ __forceinline__ void finish_pixel(const FusedParams& p, const int C, float (&d2)[CP], long long tile_base, int t,
+                                             float* stage, PixelStats& st, const float* preloaded_prior = nullptr) {
+    const long long remain = p.N - tile_base;
+    const int tile_rows = remain <= 0 ? 0 : (remain < kTilePixels ? (int)remain : kTilePixels);
+    finish_pixel_rows<CP, WANT_DIST>(p, C, d2, tile_base, tile_rows, t, stage, st, preloaded_prior);
 }
 
 // Block-level, fixed-order reduction of the per-thread statistics into one partial row.

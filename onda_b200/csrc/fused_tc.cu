@@ -1,56 +1,78 @@
-// tcgen05 implementation of the fused pass for sm_100a (D = 128 or 256, C <= 32).
+// tcgen05 implementation of the fused pass for sm_100a (64 <= D <= 256, D % 64 == 0, C <= 32).
 //
 // Why tensor cores: the CUDA-core kernel (fused_simt.cu) is issue-bound -- 21 FFMA per feature
 // element for the 19-wide contraction alone (profiles/r1_simt_v1_ncu_full.txt) -- so the distance
-// contraction moves to the 5th-generation tensor cores with an error-compensated 3xTF32 split:
-//     x' . Q  =  hi(x').hi(Q) + hi(x').lo(Q) + lo(x').hi(Q)      (fp32 accumulate in TMEM)
-// which keeps fp32-level accuracy (the dropped lo.lo term is 2^-22 relative).
+// contraction moves to the 5th-generation tensor cores with an error-compensated TF32 split:
+//     x' . Q  =  hi(x').hi(Q) + hi(x').lo(Q) + lo(x').hi(Q) + lo(x').lo(Q)      (fp32 accumulate in TMEM)
 //
-// One persistent CTA per SM, 24 warps, over a single global chunk sequence (chunk = 128 pixels x
-// 32 channels; a tile of 128 pixels is D/32 consecutive chunks):
-//   warps  0-15  workers, four groups of four; warp w%4 is the pixel quarter (the only TMEM lanes a warp
-//                may touch are 32*(w%4)..+31), w/4 the group; group g takes chunks g, g+4, g+8, ...
-//                Per chunk: (1) lane = pixel: coalesced 4-byte loads along the NCHW channel planes (the planes
-//                are only 4-byte aligned: no TMA), issued eight at a time between the phases below so that
-//                the warp never sits blocked behind the SM's miss queue; (2) raw values -> the group's
-//                shared-memory tile [pixel][channel]; (3) centred values, split into TF32 hi/lo with packed
-//                f32x2 math -> TMEM (tcgen05.st) as the A operand (lane = pixel, column = channel), and
-//                sum_j w_j x'_j^2 -> a spare TMEM column of the same lane; (4) class sums of the chunk:
-//                lane = channel, each of the group's four warps walks 32 entries of the class-sorted pixel
-//                list and adds every segment's (sum, sum of squares) to that class's shared-memory
-//                accumulators; a range that starts inside a class parks that first segment in a spare row
-//                which the warp that started the class adds after the group's barrier.  One writer per
-//                accumulator at a time, fixed summation order, no atomics.
+// Feature ingest (round 2): tensor TMA.  The NCHW channel planes are only 4-byte aligned (H*W is odd) and a tensor map
+// needs 16-byte aligned strides -- which the planes of every FOURTH channel have (4*H*W floats apart).  So the feature
+// map is described by four 3-D tensor maps, one per residue r = channel mod 4: {float index u, channel group a =
+// channel / 4, image}, strides {4, 16*H*W, 4*D*H*W} bytes, base = the 16-byte boundary at or below channel r of
+// image 0, pixel p of that channel sitting at u = p + shift_r (shift_r = 0..3 floats, fixed per map).  Box
+// coordinates are element indices and need no alignment, so ONE cp.async.bulk.tensor fetches the 128-pixel rows of
+// 8 channels (box 132 x 8 x 1, 4 extra floats of padding per row, out-of-range elements zero-filled) and four of
+// them fetch a 32-channel chunk into a ring stage: rows grouped by residue, slot 8*r + a, 528-byte pitch, the row
+// of residue r starting shift_r floats into its slot (boxes start at float index pix0: 16-byte aligned addresses).  No thread issues a global load for the features, no registers
+// hold loads in flight, and the memory-level parallelism is the ring depth (5-6 stages of 16.5 KB), not the warp
+// count.  A tile is 128 consecutive pixels of ONE image (the last tile of an image is partial).
+//
+// One persistent CTA per SM, 24 warps, over a single global chunk sequence (chunk = 128 pixels x 32 channels;
+// a tile is D/32 consecutive chunks; chunk q uses ring stage q % nstage and TMEM A stage q % 4):
+//   warp   23    producer: one thread; waits for the ring stage to be free, then issues the chunk's four tensor
+//                copies (mbarrier expect_tx / complete_tx).
+//   warps  0-7   converters, two groups of four; warp w%4 is the pixel quarter (the only TMEM lanes a warp may
+//                touch are 32*(w%4)..+31), group g takes chunks g, g+2, ...  Per chunk: lane = pixel reads the
+//                32 channel rows of the stage (consecutive lanes = consecutive words: conflict-free), releases
+//                the stage, centres, accumulates sum_j w_j x'_j^2, splits into TF32 hi/lo with packed f32x2 math
+//                and writes both with tcgen05.st into TMEM as the A operand (lane = pixel, column = channel).
+//   warps  8-15  summers, two groups of four: the class sums of the chunk straight from the ring stage,
+//                lane = channel.  With slot 8*(c%4) + c/4, 528-byte pitch and the row of residue c%4 starting
+//                shift(c%4) floats into its slot, the 32 lanes of a "same pixel, 32 channels" read hit 32 different
+//                banks when H*W is odd (bank = 4*(c/4) + shift(c%4) + pixel; the four shifts are then distinct; an even
+//                H*W costs bank conflicts here, nothing else).  Each warp walks
+//                32 entries of the class-sorted pixel list and adds every segment's (sum, sum of squares) to that
+//                class's shared-memory accumulators; a range that starts inside a class parks that first segment
+//                in a spare row which the warp that started the class adds after the group's barrier.  One
+//                writer per accumulator at a time, fixed summation order, no atomics.
 //   warps 16-19  epilogue: tcgen05.ld of the 32 accumulator columns and the partial columns of their pixel,
 //                then the common per-pixel tail (epilogue.cuh): sqrt, softmax, prior rectification, label,
 //                statistics.
 //   warps 20-21  sorter: per tile, class of every pixel (first argmax of the EMA logits) and a stable
-//                counting sort of the 128 pixels by class, published for the workers (double-buffered).
-//   warp   22    MMA issuer: per chunk 4 K-steps x 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
-//                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory (one bulk
-//                asynchronous copy in the prologue).
+//                counting sort of the 128 pixels by class, published for the summers (double-buffered).
+//   warp   22    MMA issuer: per chunk 4 K-steps x 4 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
+//                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory (bulk copies in the
+//                prologue that only this warp waits for).
 // Every mbarrier has one producer side and one consumer side that visit it phase by phase, in order.
 // Two accumulator buffers of 32 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
-// Shared memory is kept under 195 KB on purpose (tc_smem): the next carve-out step leaves 28 KB of L1 and
-// costs a quarter of the speed.
+#include <cuda.h>
+
+#include <mutex>
 #include <utility>
+
 #include "epilogue.cuh"
 
 namespace onda {
 
-constexpr int kTcWorkerWarps = 16;
+constexpr int kTcConvWarps = 8;                  // warps 0..7
+constexpr int kTcSumWarp0 = 8;                   // warps 8..15
+constexpr int kTcSumWarps = 8;
 constexpr int kTcEpiWarp0 = 16;
 constexpr int kTcSortWarp0 = 20;                 // two sorter warps, two pixels per lane
-constexpr int kTcMmaWarp = 22;                   // warp 23 is idle: 24 warps = six full warpgroups -> 80 registers per thread
-constexpr int kTcThreads = 24 * 32;
-constexpr int kTcGroups = 4;                     // worker groups = TMEM A stages = class-sum tiles
+constexpr int kTcMmaWarp = 22;
+constexpr int kTcProdWarp = 23;
+constexpr int kTcThreads = 24 * 32;              // 24 warps = six full warpgroups -> 80 registers per thread
+constexpr int kTcAStages = 4;                    // TMEM A stages (hi | lo, 64 columns each)
+constexpr int kTcSumGroups = 2;
 constexpr int kTcChunkC = 32;                    // channels per chunk
-constexpr int kTcTRow = 34;                      // floats per pixel row of a class-sum tile: 32 channels + 2 (conflict-free STS.64 and LDS.32)
+constexpr int kTcRowBytes = 528;                 // 16-byte cover of 128 floats at any 4-byte phase
+constexpr int kTcStageBytes = kTcChunkC * kTcRowBytes;
+constexpr int kTcMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kAccCol0 = kTcGroups * 64;    // accumulators after the A stages
+constexpr uint32_t kAccCol0 = kTcAStages * 64;   // accumulators after the A stages
 constexpr uint32_t kApartCol0 = kAccCol0 + 64;   // then sum_j w_j x'_j^2 of each chunk: 2 tile parities x 8 chunks, lane = pixel
-constexpr int kTcHeadFloats = kTcGroups * 3 * kTcChunkC;   // per statistic: head partials of ranges 1..3 of every group's current chunk
-constexpr uint32_t kSpinLimit = 20000000u;       // failed probes (each followed by a <=256 ns sleep) before giving up
+constexpr int kTcHeadFloats = kTcSumGroups * 2 * 3 * kTcChunkC;   // per statistic: head partials of ranges 1..3 of every group's current chunk, double-buffered over the group's chunks
+constexpr uint32_t kSpinLimit = 20000000u;       // failed probes (each followed by a sleep) before giving up
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,6 +82,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // One non-blocking probe of an mbarrier phase (test_wait: try_wait may park in the shared-memory pipeline
 // for a hardware time-out, and ~20 parked waiters starve the LDS/STS of the working warps).
@@ -100,11 +125,6 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
-__device__ __forceinline__ uint32_t cvt_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
 // packed fp32 pairs (sm_100 FADD2 / FFMA2): one instruction, two channels
 __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
     uint64_t d;
@@ -132,12 +152,6 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
-__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
-    uint64_t v;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -149,12 +163,6 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -178,24 +186,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
-
-// x[J] = feature at plane J of a pixel: 32-bit element index off0 + J * plane (one IMAD with an immediate plane index,
-// no table of offsets in registers, no dependent chain), then one IMAD.WIDE onto the base; the load bypasses L1
-// allocation (streamed once)
-template <int J>
-__device__ __forceinline__ float ldg_plane(const float* feat, unsigned off0, unsigned plane) {
-    float v;
-    const float* a = feat + (off0 + (unsigned)J * plane);      // 32-bit element index (tc_supported: the map has < 2^32 elements)
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(a));
-    return v;
+// 3-D tensor copy global -> shared (tile mode), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy) : "memory");
 }
-template <int N, int... Js>
-__device__ __forceinline__ void ldg_planes(float (&x)[N], const float* feat, unsigned off0, unsigned plane, std::integer_sequence<int, Js...>) {
-    ((x[Js] = ldg_plane<Js>(feat, off0, plane)), ...);
-}
-template <int J0, int N, int... Js>
-__device__ __forceinline__ void ldg_planes_part(float (&x)[N], const float* feat, unsigned off0, unsigned plane, std::integer_sequence<int, Js...>) {
-    ((x[J0 + Js] = ldg_plane<J0 + Js>(feat, off0, plane)), ...);
+__device__ __forceinline__ void bulk_g2s_plain(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100)
@@ -212,50 +210,68 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// slot of channel row j (0..31) of a chunk inside a ring stage: rows grouped by (j mod 4), see the header
+__host__ __device__ constexpr int ring_slot(int j) { return 8 * (j & 3) + (j >> 2); }
+
 // ---- shared-memory carve-up ------------------------------------------------------------------------
 struct TcSmem {
-    size_t bhi, blo, tiles, acc, out, mu, w, eoff, ecls, cuts, wc, cnt, red, bars, tmem_ptr, total;  // byte offsets
+    size_t bars, tmem_ptr, eoff, ecls, cuts, wc, cnt, red, out, mu, w, bhi, blo, acc, ring, total;  // byte offsets
+    int nstage;
 };
-__host__ __device__ inline TcSmem tc_smem(int D, int C, int CP, bool sums) {
+__host__ __device__ inline TcSmem tc_smem(int Dc, int C, int CP, bool sums, int nstage) {
     // Everything whose size does not depend on D or C comes first: its addresses are compile-time offsets from the
-    // shared-memory base and cost no registers (the workers have none to spare).
-    // The total matters beyond fitting: L1 is what the SM's 256 KB leave after the shared-memory carve-out, the
-    // carve-out is one of a few sizes (.., 164, 196, 228 KB), and the kernel is measurably slower with the 28 KB of L1
-    // that 228 KB leave than with the 60 KB of the 196 KB step (the feature loads straddle 128-byte lines; the
-    // second line is the next quarter's first).  Keep total + 1 KB (system) <= 196 KB.
+    // shared-memory base and cost no registers.
     TcSmem s;
     size_t o = 0;
-    s.bars = o; o += 256;                              // (2 * kTcGroups + 8) mbarriers
+    s.bars = o; o += 384;                              // 2 * kTcMaxStages + 2 * kTcAStages + 9 mbarriers
     s.tmem_ptr = o; o += 128;
     s.eoff = o; o += (size_t)2 * kTilePixels * 4;      // per tile parity: row offset of every class-sorted entry | segment-end flag
-    s.ecls = o; o += (size_t)2 * kTilePixels * 4;      // ... and its accumulator row (class * D; -1 = head segment of its range)
+    s.ecls = o; o += (size_t)2 * kTilePixels * 4;      // ... and its accumulator row (class * Dc; -1 = head segment of its range)
     s.cuts = o; o += 128;                              // ... [0] live entries, [1..3] the classes cut by the range starts 32, 64, 96
     s.wc = o; o += 640;                                // per-warp class histograms of the sorter (4 x 36)
     s.cnt = o; o += 128;
     s.red = o; o += 4 * kStatSlots * 4;
-    s.tiles = o; o += sums ? (size_t)kTcGroups * kTilePixels * kTcTRow * 4 : 0;
     s.out = o; o += (size_t)kTilePixels * (CP + 1) * 4;
-    s.mu = o; o += (size_t)D * 4;
-    s.w = o; o += (size_t)D * 4;
-    s.bhi = o; o += (size_t)32 * D * 4;
-    s.blo = o; o += (size_t)32 * D * 4;
-    s.acc = o; o += sums ? (size_t)2 * (C * D + kTcHeadFloats) * 4 : 0;   // [class * D/32 + chunk | then 3 heads per group][sum | sum of squares][32 channels]
+    o = (o + 127) / 128 * 128;
+    s.mu = o; o += (size_t)Dc * 4;
+    s.w = o; o += (size_t)Dc * 4;
+    s.bhi = o; o += (size_t)32 * Dc * 4;
+    s.blo = o; o += (size_t)32 * Dc * 4;
+    s.acc = o; o += sums ? (size_t)2 * (C * Dc + kTcHeadFloats) * 4 : 0;   // [class * Dc/32 + chunk | then 3 heads per group][sum | sum of squares][32 channels]
+    o = (o + 127) / 128 * 128;
+    s.ring = o; o += (size_t)nstage * kTcStageBytes;
     s.total = o;
+    s.nstage = nstage;
     return s;
 }
+// as many ring stages as fit under the per-CTA limit (227 KB), at most kTcMaxStages; 0 = does not fit
+__host__ inline int tc_ring_stages(int Dc, int C, int CP, bool sums) {
+    const size_t fixed = tc_smem(Dc, C, CP, sums, 0).total;
+    const size_t limit = 227 * 1024;
+    if (fixed + 3 * (size_t)kTcStageBytes > limit) return 0;
+    size_t n = (limit - fixed) / kTcStageBytes;
+    return (int)(n > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : n);
+}
+
+// the four tensor maps of the feature map (one per channel residue mod 4) and each map's shift
+struct TcMaps {
+    CUtensorMap map[4];
+    int shift[4];
+};
 
 template <int CP, int CE, bool SUMS, bool WANT_DIST, bool PROF>
-__global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedParams p, const __grid_constant__ TcMaps maps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = CE > 0 ? CE : p.C;      // CE: class count known at compile time (19 in every OnDA config) -> no k < C predication
     const int D = p.D, HW = p.HW;
-    const int NB = D / kTcChunkC;
-    const int nb_shift = NB == 8 ? 3 : 2;              // D = 256 or 128 (tc_supported)
-    const TcSmem L = tc_smem(D, C, CP, SUMS);
+    const int Dc = p.slice_channels;      // channels this CTA contracts over
+    const int NB = Dc / kTcChunkC;        // even (tc_supported)
+    const int nstage = p.nstage;
+    const int c_base = 0;                 // first channel of this CTA's slice
+    const TcSmem L = tc_smem(Dc, C, CP, SUMS, nstage);
     float* Bhi = reinterpret_cast<float*>(smem_raw + L.bhi);
     float* Blo = reinterpret_cast<float*>(smem_raw + L.blo);
-    float* Tst = reinterpret_cast<float*>(smem_raw + L.tiles);
     float* acc = reinterpret_cast<float*>(smem_raw + L.acc);
     float* out_stage = reinterpret_cast<float*>(smem_raw + L.out);
     float* mus = reinterpret_cast<float*>(smem_raw + L.mu);
@@ -267,27 +283,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     int* cnt = reinterpret_cast<int*>(smem_raw + L.cnt);
     float* red = reinterpret_cast<float*>(smem_raw + L.red);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + L.tmem_ptr);
+    const uint32_t ring = smem_u32(smem_raw + L.ring);
     const uint32_t bars = smem_u32(smem_raw + L.bars);
-    auto full_a = [&](int s) { return bars + 8u * s; };
-    auto empty_a = [&](int s) { return bars + 8u * (kTcGroups + s); };
-    auto acc_full = [&](int i) { return bars + 8u * (2 * kTcGroups + i); };
-    auto acc_empty = [&](int i) { return bars + 8u * (2 * kTcGroups + 2 + i); };
-    auto sort_ready = [&](int i) { return bars + 8u * (2 * kTcGroups + 4 + i); };
-    auto sort_free = [&](int i) { return bars + 8u * (2 * kTcGroups + 6 + i); };
-    const uint32_t btab_bar = bars + 8u * (2 * kTcGroups + 8);
+    auto ring_full = [&](int s) { return bars + 8u * s; };
+    auto ring_empty = [&](int s) { return bars + 8u * (kTcMaxStages + s); };
+    constexpr int kB0 = 2 * kTcMaxStages;
+    auto full_a = [&](int s) { return bars + 8u * (kB0 + s); };
+    auto empty_a = [&](int s) { return bars + 8u * (kB0 + kTcAStages + s); };
+    auto acc_full = [&](int i) { return bars + 8u * (kB0 + 2 * kTcAStages + i); };
+    auto acc_empty = [&](int i) { return bars + 8u * (kB0 + 2 * kTcAStages + 2 + i); };
+    auto sort_ready = [&](int i) { return bars + 8u * (kB0 + 2 * kTcAStages + 4 + i); };
+    auto sort_free = [&](int i) { return bars + 8u * (kB0 + 2 * kTcAStages + 6 + i); };
+    const uint32_t btab_bar = bars + 8u * (kB0 + 2 * kTcAStages + 8);
 
     const TableLayout T = table_layout(C, D);
     // ---- one-time setup: tables to shared memory, barriers, tensor memory
-    for (int i = tid; i < D; i += kTcThreads) {
-        mus[i] = -p.table[T.off_mu + i];      // negated: the workers centre with a packed add
-        wsm[i] = p.table[T.off_w + i];
+    for (int i = tid; i < Dc; i += kTcThreads) {
+        mus[i] = -p.table[T.off_mu + c_base + i];      // negated: the converters centre with a packed add
+        wsm[i] = p.table[T.off_w + c_base + i];
     }
     if (SUMS) {
-        for (int i = tid; i < 2 * (C * D + kTcHeadFloats); i += kTcThreads) acc[i] = 0.f;
+        for (int i = tid; i < 2 * (C * Dc + kTcHeadFloats); i += kTcThreads) acc[i] = 0.f;
         if (tid < 32) cnt[tid] = 0;
     }
     if (tid == 0) {
-        for (int s = 0; s < kTcGroups; ++s) {
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(ring_full(s), 1);                  // the producer's expect_tx arrive; the four tensor copies complete the bytes
+            mbar_init(ring_empty(s), SUMS ? 8 : 4);      // the four converter warps and the four summer warps of the chunk
+        }
+        for (int s = 0; s < kTcAStages; ++s) {
             mbar_init(full_a(s), 128);
             mbar_init(empty_a(s), 1);
         }
@@ -295,22 +319,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             mbar_init(acc_full(i), 1);
             mbar_init(acc_empty(i), 128);
             mbar_init(sort_ready(i), 64);
-            mbar_init(sort_free(i), kTcWorkerWarps);
+            mbar_init(sort_free(i), kTcSumWarps);
         }
         mbar_init(btab_bar, 1);
         fence_barrier_init();
-        // B operand tables (hi | lo, adjacent in the table and in shared memory): one bulk asynchronous copy, off
-        // everybody's critical path -- only the MMA issuer waits for it, before its first MMA
-        const uint32_t bytes = (uint32_t)(2 * 32 * D) * 4u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(btab_bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(Bhi)), "l"(p.table + T.off_qhi), "r"(bytes), "r"(btab_bar) : "memory");
+        // B operand tables (hi, lo) of this CTA's channel slice: two bulk asynchronous copies, off everybody's
+        // critical path -- only the MMA issuer waits for them, before its first MMA
+        const uint32_t bytes = (uint32_t)(32 * Dc) * 4u;
+        mbar_arrive_tx(btab_bar, 2u * bytes);
+        bulk_g2s_plain(smem_u32(Bhi), p.table + T.off_qhi + (size_t)c_base * 32, bytes, btab_bar);
+        bulk_g2s_plain(smem_u32(Blo), p.table + T.off_qlo + (size_t)c_base * 32, bytes, btab_bar);
     }
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    fence_async_smem();       // B tables were written through the generic proxy; the tensor core reads them through the async proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -319,51 +342,50 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     constexpr bool prof = PROF;       // per-warp wait counters (onda_debug_set_buffer); compiled out of the production kernel
     long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_start = PROF ? clock64() : 0;
+    const unsigned tpi = (unsigned)p.tiles_per_img;
     const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_chunks = my_tiles * NB;
-    const unsigned HWu = (unsigned)HW, Nu = (unsigned)p.N;
-
-    if (warp < kTcWorkerWarps) {
-        // =========================== workers ===========================================
+    const unsigned HWu = (unsigned)HW;
+    // tile t of this CTA -> image, first pixel, live pixels
+    auto tile_of = [&](int t, unsigned& img, unsigned& pix0, int& npx) {
+        const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
+        img = tile / tpi;
+        pix0 = (tile - img * tpi) * kTilePixels;
+        const unsigned rem = HWu - pix0;
+        npx = rem < (unsigned)kTilePixels ? (int)rem : kTilePixels;
+    };
+    if (warp < kTcConvWarps) {
+        // =========================== converters ========================================
         const int quarter = warp & 3, group = warp >> 2;
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
-        float* Tg = Tst + (size_t)group * kTilePixels * kTcTRow;
-        const uint32_t tg_lane = smem_u32(Tg) + 4u * lane;           // class sums: lane = channel of the chunk
-        const int gbar = 3 + group;                                   // named barrier of the group (128 threads)
+        const uint32_t lane_word = 4u * (uint32_t)(32 * quarter + lane);
+        int stage = group;                   // ring stage of chunk q = q % nstage, phase (q / nstage) & 1
+        uint32_t rphase = 0;
+        int t = 0, blk = group;
         float x[kTcChunkC];
-        const unsigned plane = HWu;
-        auto load_base = [&](int q) {   // address of channel b*32 of this lane's pixel in chunk q
-            const int t = q >> nb_shift, b = q & (NB - 1);
-            const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
-            unsigned n = tile * kTilePixels + 32 * quarter + lane;
-            n = n < Nu ? n : Nu - 1;         // clamp: results of padded rows are never stored (epilogue / sorter guard them)
-            const unsigned bimg = n / HWu, pix = n - bimg * HWu;
-            return (bimg * (unsigned)D + (unsigned)(b * kTcChunkC)) * HWu + pix;
-        };
-        auto issue_loads = [&](int q) { ldg_planes(x, p.feat, load_base(q), plane, std::make_integer_sequence<int, kTcChunkC>{}); };
-        if (group < total_chunks) issue_loads(group);
-        for (int q = group; q < total_chunks; q += kTcGroups) {
-            const int t = q >> nb_shift, b = q & (NB - 1);
+        for (int q = group; q < total_chunks; q += 2) {
+            if (blk >= NB) { blk -= NB; ++t; }
             const int par = t & 1;
+            const int as = q & (kTcAStages - 1);
             const uint32_t use = (uint32_t)q >> 2;
-            const long long t_it0 = prof ? clock64() : 0;
-            if (SUMS) {   // raw values into the group's tile, pixel-major, two channels per 8-byte store
-                float2* trow = reinterpret_cast<float2*>(Tg + (size_t)(32 * quarter + lane) * kTcTRow);
+            mbar_wait_t<64>(ring_full(stage), rphase, prof, dbg[0]);
+            {   // the 32 channel rows of this lane's pixel: row j sits in slot 8*(j%4) + j/4 and starts shift[j%4] floats in
+                const uint32_t sbase = ring + (uint32_t)stage * kTcStageBytes + lane_word;
 #pragma unroll
-                for (int j = 0; j < kTcChunkC / 2; ++j) trow[j] = make_float2(x[2 * j], x[2 * j + 1]);
-                named_bar_sync(gbar, 128);          // all 128 pixels of the chunk are staged
+                for (int j = 0; j < kTcChunkC; ++j) x[j] = lds32(sbase + (uint32_t)ring_slot(j) * kTcRowBytes + 4u * (uint32_t)maps.shift[j & 3]);
             }
-            if (prof) dbg[4] += clock64() - t_it0;
-            if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // accumulator and partials [par] of tile t-2 consumed
-            mbar_wait_t(empty_a(group), (use & 1) ^ 1, prof, dbg[2]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ring_empty(stage));      // this warp's reads of the stage are issued and ordered before the arrive
+            stage += 2;
+            if (stage >= nstage) { stage -= nstage; rphase ^= 1; }
+            if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[1]);   // partial columns [par] of tile t-2 consumed
+            mbar_wait_t<64>(empty_a(as), (use & 1) ^ 1, prof, dbg[2]);
             tc_fence_after();
             const long long t_cv0 = prof ? clock64() : 0;
-            const bool more = q + kTcGroups < total_chunks;
-            const unsigned nsrc = load_base(more ? q + kTcGroups : q);
             uint64_t a2 = 0;                       // sum_j w_j x'_j^2 of the even / odd channels (packed f32x2 math)
-            const uint32_t tcol = tmem_base + lane_base + (uint32_t)group * 64;
-            const ulonglong2* mu4 = reinterpret_cast<const ulonglong2*>(mus + b * kTcChunkC);     // -mu, two pairs per load
-            const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(wsm + b * kTcChunkC);
+            const uint32_t tcol = tmem_base + lane_base + (uint32_t)as * 64;
+            const ulonglong2* mu4 = reinterpret_cast<const ulonglong2*>(mus + blk * kTcChunkC);     // -mu, two pairs per load
+            const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(wsm + blk * kTcChunkC);
             const uint64_t neg1 = pack2(-1.f, -1.f);
 #pragma unroll
             for (int part = 0; part < 4; ++part) {       // eight channels at a time: bounds the live registers
@@ -388,103 +410,122 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 }
                 tc_st8(tcol + part * 8, hi);
                 tc_st8(tcol + 32 + part * 8, lo);
-                if (more) {   // the registers of channels 0..15 are free again: their next loads start here
-                    if (part == 1) ldg_planes_part<0>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 8>{});
-                    if (part == 3) ldg_planes_part<8>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 8>{});
-                }
             }
             const float a = __uint_as_float((uint32_t)a2) + __uint_as_float((uint32_t)(a2 >> 32));
-            tc_st1(tmem_base + lane_base + kApartCol0 + (uint32_t)(par * 8 + b), __float_as_uint(a));     // read by this pixel's epilogue thread
-            const long long t_cv1 = prof ? clock64() : 0;
+            tc_st1(tmem_base + lane_base + kApartCol0 + (uint32_t)(par * 8 + blk), __float_as_uint(a));     // read by this pixel's epilogue thread
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(full_a(group));
-            const long long t_cv2 = prof ? clock64() : 0;
-            // The next chunk's loads fly during the class sums.  With class sums they are issued eight at a time between
-            // the batches of the summation: 32 back-to-back loads from every warp of a group fill the SM's miss queue and
-            // the warp would sit blocked at the issue (measured: a quarter of the worker's time).
-            if (!SUMS && more) {
-                ldg_planes_part<16>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 16>{});
-            }
-            if (prof) {
-                dbg[5] += t_cv1 - t_cv0;                 // centring / splitting / tcgen05.st issue
-                dbg[6] += t_cv2 - t_cv1;                 // tcgen05.wait::st + arrive
-                dbg[0] += clock64() - t_cv2;             // issuing the next chunk's loads (acc_empty waits are negligible)
-            }
-
-            if (SUMS) {
-                // ---- class sums of this chunk's 32 channels (lane = channel).  The class-sorted pixels of the tile are cut
-                // into four ranges of 32 entries, one per warp of the group: balanced whatever the label map looks like.
-                // Lane e keeps entry e's row offset and the offset of its accumulator row in registers (broadcast by
-                // shuffle: no dependent shared-memory loads), eight loads are in flight at once, and the segment ends
-                // are a warp-uniform bit mask: an end adds the running (sum, sum of squares) to that row.  A range that
-                // starts inside a class accumulates that first segment (its "head") into a spare row -- same code, the
-                // sorter just marks those entries -- which the warp that started the class adds to the class row after
-                // the group's barrier, heads in range order.  One writer per accumulator at a time, fixed order, no
-                // atomics.
-                mbar_wait_t(sort_ready(par), ((uint32_t)t >> 1) & 1, prof, dbg[1]);
-                const long long t_seg0 = prof ? clock64() : 0;
-                const int* eo = eoff + par * kTilePixels;
-                const int* ec = ecls + par * kTilePixels;
-                const int* ct = cuts + par * 8;
-                // accumulators: row (class * NB + b), then [sum | sum of squares][32 channels]: the pair of a flush is 128 bytes apart
-                const uint32_t a1 = smem_u32(acc) + (uint32_t)(b * 64 + lane) * 4u;     // + row offset of the class (bytes, from the sorter)
-                const uint32_t head_base = (uint32_t)(C * NB + group * 3 - b) * 256u;   // head j of this group, relative to a1: + (j-1)*256
-                const int idx = 32 * quarter + lane;                                    // this warp's range: entries 32*quarter .. +31
-                int nlive = ct[0] - 32 * quarter;                                       // ct[0] = live entries of the tile
-                nlive = nlive < 0 ? 0 : (nlive > 32 ? 32 : nlive);
-                const int eo_i = eo[idx], er_i = ec[idx];
-                const unsigned endbits = __ballot_sync(0xffffffffu, eo_i & 1);          // segment ends (sorter: class end or entry 31)
-                const int myoff = eo_i & ~1;
-                const uint32_t myrow = er_i < 0 ? head_base + (uint32_t)(quarter - 1) * 256u : (uint32_t)er_i;   // accumulator row (bytes) of this entry's segment
-                float s1 = 0.f, s2 = 0.f;
+            mbar_arrive(full_a(as));
+            if (prof) dbg[3] += clock64() - t_cv0;         // centring / splitting / tcgen05.st / wait::st
+            blk += 2;
+        }
+    } else if (SUMS && warp < kTcSumWarp0 + kTcSumWarps) {
+        // =========================== summers ===========================================
+        // Class sums of the chunk's 32 channels (lane = channel), read straight from the ring stage.  The class-sorted
+        // pixels of the tile are cut into four ranges of 32 entries, one per warp of the group: balanced whatever the
+        // label map looks like.  The pixel offsets of the entries come four at a time from warp-uniform (broadcast)
+        // 16-byte loads, sixteen feature loads are in flight at once, and the segment ends are a warp-uniform bit mask:
+        // an end adds the running (sum, sum of squares) to the segment's accumulator row.  A range that
+        // starts inside a class accumulates that first segment (its "head") into a spare row -- same code, the sorter
+        // just marks those entries -- which the warp that started the class adds to the class row after the group's
+        // barrier, heads in range order.  One writer per accumulator at a time, fixed order, no atomics.
+        const int sw = warp - kTcSumWarp0;
+        const int quarter = sw & 3, group = sw >> 2;        // quarter = which 32 sorted entries; group g takes chunks g, g+2, ..
+        const int gbar = 3 + group;                         // named barrier of the group (128 threads)
+        int stage = group;
+        uint32_t rphase = 0;
+        int t = 0, blk = group;
+        int hp = 0;                                         // head buffer of this chunk (alternates over the group's chunks)
+        const uint32_t lane_off = (uint32_t)ring_slot(lane) * kTcRowBytes + 4u * (uint32_t)maps.shift[lane & 3];   // pixel 0 of this lane's channel row
+        const int idx = 32 * quarter + lane;                // this warp's range: entries 32*quarter .. +31
+        for (int q = group; q < total_chunks; q += 2, hp ^= 1) {
+            if (blk >= NB) { blk -= NB; ++t; }
+            const int par = t & 1;
+            mbar_wait_t<64>(sort_ready(par), ((uint32_t)t >> 1) & 1, prof, dbg[1]);
+            mbar_wait_t<64>(ring_full(stage), rphase, prof, dbg[0]);
+            const long long t_seg0 = prof ? clock64() : 0;
+            const uint32_t row_lane = ring + (uint32_t)stage * kTcStageBytes + lane_off;
+            const uint32_t eo = smem_u32(eoff + par * kTilePixels + 32 * quarter);     // byte offsets of this range's 32 pixels in a row
+            const int* ct = cuts + par * 8;
+            // accumulators: row (class * NB + blk), then [sum | sum of squares][32 channels]: the pair of a flush is 128 bytes apart
+            const uint32_t a1 = smem_u32(acc) + (uint32_t)(blk * 64 + lane) * 4u;     // + row offset of the class (bytes, from the sorter)
+            const uint32_t head_base = (uint32_t)(C * NB + (group * 2 + hp) * 3 - blk) * 256u;   // head j of this group's chunk, relative to a1: + (j-1)*256
+            int nlive = ct[0] - 32 * quarter;                                         // ct[0] = live entries of the tile
+            nlive = nlive < 0 ? 0 : (nlive > 32 ? 32 : nlive);
+            const int er_i = ecls[par * kTilePixels + idx];                           // bit 0: segment end, bit 1: head segment, else class row offset
+            const unsigned endbits = __ballot_sync(0xffffffffu, er_i & 1);            // segment ends (sorter: class end or entry 31)
+            const uint32_t myrow = (er_i & 2) ? head_base + (uint32_t)(quarter - 1) * 256u : (uint32_t)(er_i & ~3);   // accumulator row (bytes) of this entry's segment
+            // The accumulator pair of the running segment is fetched when the segment starts, so a flush is an add and
+            // two stores; entries past the last live one need no guard: that one ends a segment, so whatever they add
+            // to the running pair is never flushed (their rows are the zero-filled padding of the tile anyway).
+            uint32_t cur = a1 + (uint32_t)__shfl_sync(0xffffffffu, myrow, 0);
+            float c1 = lds32(cur), c2 = lds32(cur + 128u);
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int e0 = 0; e0 < 32; e0 += 8) {
-                    if (more) {
-                        if (e0 == 0) ldg_planes_part<16>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 8>{});
-                        if (e0 == 16) ldg_planes_part<24>(x, p.feat, nsrc, plane, std::make_integer_sequence<int, 8>{});
-                    }
-                    if (e0 >= nlive) continue;
-                    float xv[8];
+            for (int h = 0; h < 2; ++h) {            // 16 entries at a time: all their loads in flight at once
+                if (16 * h >= nlive) continue;
+                int4 ov[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const uint32_t ad = tg_lane + (uint32_t)__shfl_sync(0xffffffffu, myoff, e0 + e);
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[e]) : "r"(ad));
-                    }
-                    // entries past the last live one need no guard: that one ends a segment, so whatever they add to
-                    // the running pair is never flushed
+                for (int i = 0; i < 4; ++i)          // warp-uniform address: one broadcast 16-byte load gives four offsets
+                    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(ov[i].x), "=r"(ov[i].y), "=r"(ov[i].z), "=r"(ov[i].w) : "r"(eo + 64u * h + 16u * i));
+                float xv[16];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        s1 += xv[e];
-                        s2 = fmaf(xv[e], xv[e], s2);
-                        if (endbits & (1u << (e0 + e))) {
-                            const uint32_t ad = a1 + __shfl_sync(0xffffffffu, myrow, e0 + e);
-                            sts32(ad, lds32(ad) + s1);
-                            sts32(ad + 128u, lds32(ad + 128u) + s2);
-                            s1 = 0.f;
-                            s2 = 0.f;
+                for (int i = 0; i < 4; ++i) {
+                    xv[4 * i + 0] = lds32(row_lane + (uint32_t)ov[i].x);
+                    xv[4 * i + 1] = lds32(row_lane + (uint32_t)ov[i].y);
+                    xv[4 * i + 2] = lds32(row_lane + (uint32_t)ov[i].z);
+                    xv[4 * i + 3] = lds32(row_lane + (uint32_t)ov[i].w);
+                }
+                if (h == 1 || nlive <= 16) {         // the stage's last reads are issued: release it (ordered before the arrive)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ring_empty(stage));
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    s1 += xv[e];
+                    s2 = fmaf(xv[e], xv[e], s2);
+                    if (endbits & (1u << (16 * h + e))) {
+                        sts32(cur, c1 + s1);
+                        sts32(cur + 128u, c2 + s2);
+                        s1 = 0.f;
+                        s2 = 0.f;
+                        if (16 * h + e < 31) {       // the next segment's accumulators
+                            cur = a1 + (uint32_t)__shfl_sync(0xffffffffu, myrow, 16 * h + e + 1);
+                            c1 = lds32(cur);
+                            c2 = lds32(cur + 128u);
                         }
                     }
                 }
-                if (prof) dbg[3] += clock64() - t_seg0;
-                named_bar_sync(gbar, 128);          // the group is done reading its tile; all heads are complete
-                {   // move the heads of the classes this warp started into their class rows
-                    const int hj = (lane >= 1 && lane < 4) ? ct[lane] : -1;
-                    unsigned m = __ballot_sync(0xffffffffu, hj >= 0 && (hj >> 8) == quarter);
-                    while (m) {
-                        const int j = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int k = __shfl_sync(0xffffffffu, hj, j) & 0xff;
-                        const uint32_t hd = a1 + head_base + (uint32_t)(j - 1) * 256u, ad = a1 + (uint32_t)(k * NB) * 256u;
-                        sts32(ad, lds32(ad) + lds32(hd));
-                        sts32(ad + 128u, lds32(ad + 128u) + lds32(hd + 128u));
-                        sts32(hd, 0.f);
-                        sts32(hd + 128u, 0.f);
-                    }
+            }
+            if (nlive == 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ring_empty(stage));
+            }
+            stage += 2;
+            if (stage >= nstage) { stage -= nstage; rphase ^= 1; }
+            if (prof) dbg[3] += clock64() - t_seg0;
+            named_bar_sync(gbar, 128);          // all heads of this chunk are complete
+            {   // move the heads of the classes this warp started into their class rows
+                const int hj = (lane >= 1 && lane < 4) ? ct[lane] : -1;
+                unsigned m = __ballot_sync(0xffffffffu, hj >= 0 && (hj >> 8) == quarter);
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int k = __shfl_sync(0xffffffffu, hj, j) & 0xff;
+                    const uint32_t hd = a1 + head_base + (uint32_t)(j - 1) * 256u, ad = a1 + (uint32_t)(k * NB) * 256u;
+                    sts32(ad, lds32(ad) + lds32(hd));
+                    sts32(ad + 128u, lds32(ad + 128u) + lds32(hd + 128u));
+                    sts32(hd, 0.f);
+                    sts32(hd + 128u, 0.f);
                 }
-                if (q + kTcGroups >= total_chunks || ((q + kTcGroups) >> nb_shift) != t) {   // last chunk of this tile for the group
-                    if (lane == 0) mbar_arrive(sort_free(par));
-                }
+            }
+            // The head rows alternate between two buffers, so the next chunk's heads cannot meet this chunk's moves; the
+            // class rows of a chunk are revisited NB/2 chunks later, behind at least one more group barrier -- except when
+            // the group owns a single chunk per tile (NB == 2): then the next chunk flushes into the very same rows.
+            if (NB == 2) named_bar_sync(gbar, 128);
+            blk += 2;
+            if (blk >= NB) {                    // that was this group's last chunk of the tile
+                if (lane == 0) mbar_arrive(sort_free(par));
             }
         }
     } else if (warp == kTcMmaWarp) {
@@ -492,32 +533,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(128, 32);
             const uint32_t bhi_addr = smem_u32(Bhi), blo_addr = smem_u32(Blo);
-            mbar_wait<32>(btab_bar, 0);             // the B tables have landed (bulk copy of the prologue)
+            mbar_wait<32>(btab_bar, 0);             // the B tables have landed (bulk copies of the prologue)
+            int q = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 const int par = t & 1;
                 if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + kAccCol0 + (uint32_t)par * 32;
-                for (int b = 0; b < NB; ++b) {
-                    const int q = t * NB + b;
-                    const int stage = q & 3;
+                for (int b = 0; b < NB; ++b, ++q) {
+                    const int as = q & (kTcAStages - 1);
                     const uint32_t use = (uint32_t)q >> 2;
-                    mbar_wait_t<32>(full_a(stage), use & 1, prof, dbg[1]);
+                    mbar_wait_t<32>(full_a(as), use & 1, prof, dbg[1]);
                     tc_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t a_hi = tmem_base + (uint32_t)stage * 64 + ks * 8;
+                        const uint32_t a_hi = tmem_base + (uint32_t)as * 64 + ks * 8;
                         const uint32_t a_lo = a_hi + 32;
                         const uint32_t koff = (uint32_t)((b * kTcChunkC + ks * 8) / 4) * 512u;   // 4 channels = one 512-byte slab
                         const uint64_t d_hi = make_bdesc(bhi_addr + koff, 512, 128);
                         const uint64_t d_lo = make_bdesc(blo_addr + koff, 512, 128);
-                        tc_mma_tf32_ts(dcol, a_hi, d_hi, idesc, (b | ks) != 0);
-                        tc_mma_tf32_ts(dcol, a_hi, d_lo, idesc, 1);
+                        tc_mma_tf32_ts(dcol, a_lo, d_lo, idesc, (b | ks) != 0);     // smallest terms first
                         tc_mma_tf32_ts(dcol, a_lo, d_hi, idesc, 1);
+                        tc_mma_tf32_ts(dcol, a_hi, d_lo, idesc, 1);
+                        tc_mma_tf32_ts(dcol, a_hi, d_hi, idesc, 1);
                     }
-                    tc_commit(empty_a(stage));          // A stage reusable once these MMAs retire
+                    tc_commit(empty_a(as));             // A stage reusable once these MMAs retire
                 }
                 tc_commit(acc_full(par));               // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else if (warp == kTcProdWarp) {
+        // =========================== producer ===========================================
+        // One thread.  Chunk (tile, 32 channels from cb) = four tensor copies, one per channel residue r: box of 132
+        // floats x 8 channel groups starting at float index pix0 (a 16-byte aligned address; pixel pix0 lands shift_r
+        // floats into the row, indices past the row's end are zero-filled), channel group cb / 4, image img.
+        if (lane == 0) {
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+#pragma unroll
+            for (int r = 0; r < 4; ++r) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.map[r]) : "memory");
+            int stage = 0;
+            uint32_t rphase = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                unsigned img, pix0;
+                int npx;
+                tile_of(t, img, pix0, npx);
+                for (int b = 0; b < NB; ++b) {
+                    mbar_wait_t<64>(ring_empty(stage), rphase ^ 1, prof, dbg[0]);
+                    const uint32_t dst = ring + (uint32_t)stage * kTcStageBytes;
+                    const uint32_t bar = ring_full(stage);
+                    mbar_arrive_tx(bar, (uint32_t)kTcStageBytes);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        tma_load_3d(dst + (uint32_t)(8 * r) * kTcRowBytes, &maps.map[r], (int)pix0, (c_base + b * kTcChunkC) / 4,
+                                    (int)img, bar, policy);
+                    if (++stage == nstage) { stage = 0; rphase ^= 1; }
+                }
             }
         }
         __syncwarp();
@@ -529,18 +601,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         const float* bias = p.table + T.off_bias;
         for (int t = 0; t < my_tiles; ++t) {
             const int par = t & 1;
-            const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+            unsigned img, pix0;
+            int npx;
+            tile_of(t, img, pix0, npx);
+            const long long n0 = (long long)img * HW + pix0;
             float pri[CP];
             {   // prior row of this pixel: issued before the wait so its latency hides behind the MMAs
-                const long long n = tile * kTilePixels + et;
-                if (n < p.N && p.prior != nullptr && (p.labels != nullptr || p.soft != nullptr)) {
-                    load_pixel_row<CP>(p.prior, C, HW, n, pri);
+                if (et < npx && p.prior != nullptr && (p.labels != nullptr || p.soft != nullptr)) {
+                    load_pixel_row<CP>(p.prior, C, HW, n0 + et, pri);
                 } else {
 #pragma unroll
                     for (int k = 0; k < CP; ++k) pri[k] = 0.f;
                 }
             }
-            mbar_wait_t<800>(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
+            mbar_wait_t<400>(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
             tc_fence_after();
             uint32_t dv[32];
             tc_ld32(tmem_base + lane_base + kAccCol0 + (uint32_t)par * 32, dv);
@@ -555,7 +629,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             float d2[CP];
 #pragma unroll
             for (int k = 0; k < CP; ++k) d2[k] = (a_tot + __ldg(bias + k)) + __uint_as_float(dv[k]);
-            finish_pixel<CP, WANT_DIST>(p, C, d2, tile * kTilePixels, et, out_stage, st, pri);
+            finish_pixel_rows<CP, WANT_DIST>(p, C, d2, n0, npx, et, out_stage, st, pri);
         }
         // fixed-order reduction of the statistics over the four epilogue warps
         {
@@ -578,30 +652,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         // =========================== sorter ================================================
         // Per tile: class of every pixel = first argmax of the EMA logits (prototype_handler.py:83-86), then a stable
         // counting sort of the 128 pixels by class (padding pixels form bucket 32, last).  Two warps, two pixels per
-        // lane: "virtual warp" v = 2*sw + r owns pixels 32*v .. 32*v+31.  Published per tile parity: row offset and
+        // lane: "virtual warp" v = 2*sw + r owns pixels 32*v .. 32*v+31.  Published per tile parity: pixel offset and
         // class of every sorted entry, and the cuts of the sorted order into four ranges at class boundaries (one
-        // range per warp of a worker group).
+        // range per warp of a summer group).
         const int sw = warp - kTcSortWarp0;
         float lv[2][CP];
         auto fetch_logits = [&](int t) {   // the logits of tile t+1 are fetched while tile t is being sorted
+            if (t >= my_tiles) return;
+            unsigned img, pix0;
+            int npx;
+            tile_of(t, img, pix0, npx);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const long long n = ((long long)blockIdx.x + (long long)t * gridDim.x) * kTilePixels + 32 * (2 * sw + r) + lane;
-                if (t < my_tiles && n < p.N) load_pixel_row<CP>(p.logits, C, HW, n, lv[r]);
+                const int m = 32 * (2 * sw + r) + lane;
+                if (m < npx) load_pixel_row<CP>(p.logits, C, HW, (long long)img * HW + pix0 + m, lv[r]);
             }
         };
         fetch_logits(0);
         const unsigned lt_mask = (1u << lane) - 1u;
         for (int t = 0; t < my_tiles; ++t) {
             const int par = t & 1;
-            const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+            unsigned img, pix0;
+            int npx;
+            tile_of(t, img, pix0, npx);
             int y[2], bucket[2];
             unsigned peers[2];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int v = 2 * sw + r;
-                const long long n = tile * kTilePixels + 32 * v + lane;
-                y[r] = (n < p.N) ? first_argmax<CP>(lv[r], C) : -1;
+                y[r] = (32 * v + lane < npx) ? first_argmax<CP>(lv[r], C) : -1;
                 bucket[r] = y[r] < 0 ? 32 : y[r];
                 peers[r] = __match_any_sync(0xffffffffu, bucket[r]);
                 wc[v * 36 + lane] = 0;
@@ -622,8 +701,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const int n_valid = __shfl_sync(0xffffffffu, incl, 31);
             const int cstart = incl - tot;
             const bool has = tot > 0 && lane < C;
-            // the ranges of the four worker warps start at entries 32, 64, 96: cutcls[c] = the class that runs across
-            // entry 32*c | the worker warp holding that class's first entry << 8, or -1 when a class starts there
+            // the ranges of the four summer warps start at entries 32, 64, 96: cutcls[c] = the class that runs across
+            // entry 32*c | the summer warp holding that class's first entry << 8, or -1 when a class starts there
             int cutcls[4];
 #pragma unroll
             for (int c = 1; c < 4; ++c) {
@@ -632,7 +711,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 const int val = __shfl_sync(0xffffffffu, lane | ((cstart >> 5) << 8), who ? __ffs(who) - 1 : 0);
                 cutcls[c] = who ? val : -1;
             }
-            if (t >= 2) mbar_wait_t<800>(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // workers are done with tile t-2
+            if (t >= 2) mbar_wait_t<400>(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // summers are done with tile t-2
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int v = 2 * sw + r;
@@ -644,8 +723,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 const bool valid = bucket[r] != 32;
                 const bool seg_end = valid && (pos == cs + ct_ - 1 || (pos & 31) == 31);      // last of its class, or of its range
                 const bool in_head = valid && cs < (pos & ~31);                                // the class began in an earlier range
-                eoff[par * kTilePixels + pos] = ((32 * v + lane) * (kTcTRow * 4)) | (seg_end ? 1 : 0);   // row offset (even) | end flag
-                ecls[par * kTilePixels + pos] = in_head ? -1 : y[r] * NB * 256;                // accumulator row offset (bytes), -1 = the range's head
+                eoff[par * kTilePixels + pos] = (32 * v + lane) * 4;                          // byte offset of the pixel in a channel row
+                // accumulator row offset of the entry's class (bytes, a multiple of 256) | bit 1: the class began in an
+                // earlier range (head segment) | bit 0: segment end
+                ecls[par * kTilePixels + pos] = (valid ? y[r] * NB * 256 : 0) | (in_head || !valid ? 2 : 0) | (seg_end ? 1 : 0);
             }
             if (sw == 0) {
                 if (lane < 4) cuts[par * 8 + lane] = lane == 0 ? n_valid : (lane == 1 ? cutcls[1] : (lane == 2 ? cutcls[2] : cutcls[3]));
@@ -666,10 +747,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     __syncthreads();
     if (SUMS) {
         float* out = p.cta_partials + (size_t)blockIdx.x * sums_floats(C, D);
-        const int cd = C * D;
+        const int cd = C * Dc;
         for (int i = tid; i < 2 * cd; i += kTcThreads) {     // out: [sum | sum of squares][class][D]
-            const int stat = i >= cd, rem = i - stat * cd, k = rem / D, j = rem - k * D;
-            out[i] = acc[((k * NB + (j >> 5)) * 2 + stat) * 32 + (j & 31)];
+            const int stat = i >= cd, rem = i - stat * cd, k = rem / Dc, j = rem - k * Dc;
+            out[(size_t)(stat * C + k) * D + c_base + j] = acc[((k * NB + (j >> 5)) * 2 + stat) * 32 + (j & 31)];
         }
         if (tid < C) out[(size_t)2 * C * D + tid] = (float)cnt[tid];
     }
@@ -681,20 +762,80 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
 
 // ---- host side -----------------------------------------------------------------------------------------
 bool tc_supported(int B, int D, int HW, int C) {
-    if ((unsigned long long)B * D * HW >= (1ull << 32)) return false;            // 32-bit element offsets in the workers
-    if (!(D % 128 == 0 && D >= 128 && D <= 256 && C >= 1 && C <= 32)) return false;   // D/64 block pairs: 2 or 4
-    return tc_smem(D, C, padded_classes(C), true).total <= 227 * 1024;   // per-CTA shared-memory limit on sm_100
+    if (!(D % 64 == 0 && D >= 64 && D <= 256 && C >= 1 && C <= 32)) return false;
+    return tc_ring_stages(D, C, padded_classes(C), true) >= 3;
 }
+
+int tc_tiles(int B, int HW) { return B * ((HW + kTilePixels - 1) / kTilePixels); }
 
 int tc_grid(int tiles, int sms) { return tiles < sms ? tiles : sms; }
 
+// ---- tensor maps of the feature map (see the header): built with the driver's cuTensorMapEncodeTiled, fetched through
+// the runtime so the library does not link libcuda; the last few encodings are kept (a training step alternates
+// between a handful of feature buffers).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int tc_make_maps(const float* feat, int B, int D, int HW, TcMaps* out) {
+    struct Entry { const float* feat; int B, D, HW, dev; TcMaps maps; };
+    constexpr int kEntries = 8;
+    static Entry cache[kEntries];
+    static int used = 0, next = 0;
+    static std::mutex mu;
+    static EncodeTiledFn encode = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    const int dev = current_device();
+    for (int i = 0; i < used; ++i) {
+        const Entry& e = cache[i];
+        if (e.feat == feat && e.B == B && e.D == D && e.HW == HW && e.dev == dev) { *out = e.maps; return ONDA_OK; }
+    }
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ONDA_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        ONDA_REQUIRE(q == cudaDriverEntryPointSuccess && fn != nullptr, "tcgen05 kernel: the driver does not export cuTensorMapEncodeTiled");
+        encode = (EncodeTiledFn)fn;
+    }
+    Entry e;
+    e.feat = feat; e.B = B; e.D = D; e.HW = HW; e.dev = dev;
+    for (int r = 0; r < 4; ++r) {
+        const uintptr_t first = reinterpret_cast<uintptr_t>(feat + (size_t)r * HW);       // channel r of image 0, pixel 0
+        const uintptr_t base = first & ~(uintptr_t)15;
+        const int shift = (int)((first - base) >> 2);
+        const cuuint64_t dims[3] = {(cuuint64_t)HW + (cuuint64_t)shift, (cuuint64_t)(D / 4), (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)16 * HW, (cuuint64_t)4 * D * HW};
+        const cuuint32_t box[3] = {kTcRowBytes / 4, 8, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult rc = encode(&e.maps.map[r], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, reinterpret_cast<void*>(base), dims, strides,
+                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        ONDA_REQUIRE(rc == CUDA_SUCCESS, "tcgen05 kernel: cuTensorMapEncodeTiled failed (%d) for B=%d D=%d HW=%d", (int)rc, B, D, HW);
+        e.maps.shift[r] = shift;
+    }
+    cache[next] = e;
+    next = (next + 1) % kEntries;
+    if (used < kEntries) ++used;
+    *out = e.maps;
+    return ONDA_OK;
+}
+
 template <int CP, int CE, bool SUMS, bool WANT_DIST, bool PROF>
-static int launch_tc(const FusedParams& p, int grid, cudaStream_t stream) {
+static int launch_tc(FusedParams p, int grid, cudaStream_t stream) {
     auto kern = fused_tc_kernel<CP, CE, SUMS, WANT_DIST, PROF>;
-    const size_t smem = tc_smem(p.D, p.C, CP, SUMS).total;
-    ONDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.nstage = tc_ring_stages(p.slice_channels, p.C, CP, SUMS);
+    const size_t smem = tc_smem(p.slice_channels, p.C, CP, SUMS, p.nstage).total;
+    static size_t smem_set[kMaxDevices] = {};     // per instantiation and device: raise the attribute only when a launch needs more
+    const int dev = current_device();
+    if (smem > smem_set[dev]) {
+        ONDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[dev] = smem;
+    }
+    TcMaps maps;
+    const int rc = tc_make_maps(p.feat, p.B, p.D, p.HW, &maps);
+    if (rc != ONDA_OK) return rc;
     timing_begin(stream);
-    kern<<<grid, kTcThreads, smem, stream>>>(p);
+    kern<<<grid, kTcThreads, smem, stream>>>(p, maps);
     timing_end(stream);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);

@@ -21,10 +21,11 @@ torch.cuda.synchronize()
 lib.onda_debug_set_buffer(None)
 d = buf.view(148, 32, 8).double().cpu()
 tot = d[:, :, 7]
-names = {"worker": (0, 16, ["wait acc_empty + load issue", "wait sort_ready", "wait empty_a(mma)", "class-sum phase", "staging + group barrier 1", "convert + tcgen05.st issue", "tcgen05.wait::st + arrive"]),
-         "epilogue": (16, 20, ["wait acc_full"]), "sorter": (20, 24, ["wait sort_free"]),
-         "mma": (24, 25, ["wait acc_empty", "wait full_a"])}
-print("mean total cycles per warp:", tot[:, :25].mean().item())
+names = {"converter": (0, 8, ["wait ring_full", "wait acc_empty", "wait empty_a(mma)", "convert + tcgen05.st + wait::st"]),
+         "summer": (8, 16, ["wait ring_full", "wait sort_ready", "-", "class-sum loop"]),
+         "epilogue": (16, 20, ["wait acc_full"]), "sorter": (20, 22, ["wait sort_free"]),
+         "mma": (22, 23, ["wait acc_empty", "wait full_a"]), "producer": (23, 24, ["wait ring_empty"])}
+print("mean total cycles per warp:", tot[:, :24].mean().item())
 for role, (a, b, labels) in names.items():
     t = tot[:, a:b].mean().item()
     print(f"{role:9s} total {t:10.0f} cyc")
