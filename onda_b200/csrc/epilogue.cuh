@@ -63,6 +63,13 @@ __device__ __forceinline__ void load_pixel_row(const float* base, int C, int HW,
     }
 }
 
+// Same for a pixel whose class-0 element is already addressed: `lp` = &base[(img * C) * HW + pixel]; 32-bit offsets.
+template <int CP>
+__device__ __forceinline__ void load_pixel_row_at(const float* lp, int C, unsigned hw, float (&v)[CP]) {
+#pragma unroll
+    for (int k = 0; k < CP; ++k) v[k] = (k < C) ? __ldg(lp + (unsigned)k * hw) : 0.f;
+}
+
 // First maximal index with torch semantics (prototype_handler.onehot, prototype_handler.py:83-86).
 template <int CP>
 __device__ __forceinline__ int first_argmax(const float (&v)[CP], int C) {
@@ -72,6 +79,22 @@ __device__ __forceinline__ int first_argmax(const float (&v)[CP], int C) {
     for (int k = 1; k < CP; ++k)
         if (k < C && torch_greater(v[k], best)) { best = v[k]; arg = k; }
     return arg;
+}
+
+// Same result, cheaper in the common case: plain greater-than scan, and only a row that contains a NaN takes the
+// full torch rule (first NaN wins).
+template <int CP>
+__device__ __forceinline__ int first_argmax_fast(const float (&v)[CP], int C) {
+    float best = v[0];
+    int arg = 0;
+    bool has_nan = v[0] != v[0];
+#pragma unroll
+    for (int k = 1; k < CP; ++k)
+        if (k < C) {
+            has_nan |= v[k] != v[k];
+            if (v[k] > best) { best = v[k]; arg = k; }
+        }
+    return has_nan ? first_argmax<CP>(v, C) : arg;
 }
 
 // ---- fast single-instruction math (MUFU, flush-to-zero forms: no denormal fix-up code): relative error ~2^-22,

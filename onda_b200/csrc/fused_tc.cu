@@ -3,7 +3,8 @@
 // Why tensor cores: the CUDA-core kernel (fused_simt.cu) is issue-bound -- 21 FFMA per feature
 // element for the 19-wide contraction alone (profiles/r1_simt_v1_ncu_full.txt) -- so the distance
 // contraction moves to the 5th-generation tensor cores with an error-compensated TF32 split:
-//     x' . Q  =  hi(x').hi(Q) + hi(x').lo(Q) + lo(x').hi(Q) + lo(x').lo(Q)      (fp32 accumulate in TMEM)
+//     x' . Q  =  hi(x').hi(Q) + hi(x').lo(Q) + lo(x').hi(Q)      (fp32 accumulate in TMEM; the dropped
+// lo.lo term is 2^-22 relative)
 //
 // Feature ingest (round 2): tensor TMA.  The NCHW channel planes are only 4-byte aligned (H*W is odd) and a tensor map
 // needs 16-byte aligned strides -- which the planes of every FOURTH channel have (4*H*W floats apart).  So the feature
@@ -17,35 +18,38 @@
 // hold loads in flight, and the memory-level parallelism is the ring depth (5-6 stages of 16.5 KB), not the warp
 // count.  A tile is 128 consecutive pixels of ONE image (the last tile of an image is partial).
 //
-// One persistent CTA per SM, 24 warps, over a single global chunk sequence (chunk = 128 pixels x 32 channels;
+// One persistent CTA per SM, 32 warps, over a single global chunk sequence (chunk = 128 pixels x 32 channels;
 // a tile is D/32 consecutive chunks; chunk q uses ring stage q % nstage and TMEM A stage q % 4):
-//   warp   23    producer: one thread; waits for the ring stage to be free, then issues the chunk's four tensor
+//   warp   31    producer: one thread; waits for the ring stage to be free, then issues the chunk's four tensor
 //                copies (mbarrier expect_tx / complete_tx).
 //   warps  0-7   converters, two groups of four; warp w%4 is the pixel quarter (the only TMEM lanes a warp may
 //                touch are 32*(w%4)..+31), group g takes chunks g, g+2, ...  Per chunk: lane = pixel reads the
 //                32 channel rows of the stage (consecutive lanes = consecutive words: conflict-free), releases
 //                the stage, centres, accumulates sum_j w_j x'_j^2, splits into TF32 hi/lo with packed f32x2 math
 //                and writes both with tcgen05.st into TMEM as the A operand (lane = pixel, column = channel).
-//   warps  8-15  summers, two groups of four: the class sums of the chunk straight from the ring stage,
-//                lane = channel.  With slot 8*(c%4) + c/4, 528-byte pitch and the row of residue c%4 starting
-//                shift(c%4) floats into its slot, the 32 lanes of a "same pixel, 32 channels" read hit 32 different
-//                banks when H*W is odd (bank = 4*(c/4) + shift(c%4) + pixel; the four shifts are then distinct; an even
-//                H*W costs bank conflicts here, nothing else).  Each warp walks
+//   warps  8-23  summers, four groups of four; group g takes the chunks g, g+4, .. of every tile: the class sums of
+//                the chunk straight from the ring stage, lane = channel.  With slot 8*(c%4) + c/4, 528-byte pitch and
+//                the row of residue c%4 starting shift(c%4) floats into its slot, the 32 lanes of a "same pixel, 32
+//                channels" read hit 32 different banks when H*W is odd (bank = 4*(c/4) + shift(c%4) + pixel; the four
+//                shifts are then distinct; an even H*W costs bank conflicts here, nothing else).  Each warp walks
 //                32 entries of the class-sorted pixel list and adds every segment's (sum, sum of squares) to that
 //                class's shared-memory accumulators; a range that starts inside a class parks that first segment
 //                in a spare row which the warp that started the class adds after the group's barrier.  One
 //                writer per accumulator at a time, fixed summation order, no atomics.
-//   warps 16-19  epilogue: tcgen05.ld of the 32 accumulator columns and the partial columns of their pixel,
+//   warps 24-27  epilogue: tcgen05.ld of the 32 accumulator columns and the partial columns of their pixel,
 //                then the common per-pixel tail (epilogue.cuh): sqrt, softmax, prior rectification, label,
 //                statistics.
-//   warps 20-21  sorter: per tile, class of every pixel (first argmax of the EMA logits) and a stable
+//   warps 28-29  sorter: per tile, class of every pixel (first argmax of the EMA logits) and a stable
 //                counting sort of the 128 pixels by class, published for the summers (double-buffered).
-//   warp   22    MMA issuer: per chunk 4 K-steps x 4 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
+//   warp   30    MMA issuer: per chunk 4 K-steps x 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
 //                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory (bulk copies in the
 //                prologue that only this warp waits for).
+// The register file is re-split after the prologue (setmaxnreg): converters 72, summers 56, epilogue 80, the rest 64.
 // Every mbarrier has one producer side and one consumer side that visit it phase by phase, in order.
 // Two accumulator buffers of 32 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
 #include <cuda.h>
+
+#include <stdlib.h>
 
 #include <mutex>
 #include <utility>
@@ -54,16 +58,20 @@
 
 namespace onda {
 
-constexpr int kTcConvWarps = 8;                  // warps 0..7
-constexpr int kTcSumWarp0 = 8;                   // warps 8..15
-constexpr int kTcSumWarps = 8;
-constexpr int kTcEpiWarp0 = 16;
-constexpr int kTcSortWarp0 = 20;                 // two sorter warps, two pixels per lane
-constexpr int kTcMmaWarp = 22;
-constexpr int kTcProdWarp = 23;
-constexpr int kTcThreads = 24 * 32;              // 24 warps = six full warpgroups -> 80 registers per thread
+// Warp roles are aligned to warpgroups (four warps) because the register budget is re-split per warpgroup
+// (setmaxnreg): 1024 threads start with 64 registers each.
+constexpr int kTcConvGroups = 2;
+constexpr int kTcConvWarps = 4 * kTcConvGroups;  // warps 0..7    (warpgroups 0-1)
+constexpr int kTcSumWarp0 = 8;                   // warps 8..23   (warpgroups 2-5)
+constexpr int kTcSumGroups = 4;
+constexpr int kTcSumWarps = 4 * kTcSumGroups;
+constexpr int kTcEpiWarp0 = 24;                  // warps 24..27  (warpgroup 6); a multiple of 4: warp w may touch TMEM lanes 32*(w%4)..+31
+constexpr int kTcSortWarp0 = 28;                 // warps 28..29: two sorter warps, two pixels per lane
+constexpr int kTcMmaWarp = 30;
+constexpr int kTcProdWarp = 31;
+constexpr int kTcThreads = 32 * 32;
+constexpr int kTcRegsConv = 72, kTcRegsSum = 56, kTcRegsEpi = 80;   // x 256 / 512 / 128 threads, + 128 x 64 for the last warpgroup = 65536
 constexpr int kTcAStages = 4;                    // TMEM A stages (hi | lo, 64 columns each)
-constexpr int kTcSumGroups = 2;
 constexpr int kTcChunkC = 32;                    // channels per chunk
 constexpr int kTcRowBytes = 528;                 // 16-byte cover of 128 floats at any 4-byte phase
 constexpr int kTcStageBytes = kTcChunkC * kTcRowBytes;
@@ -97,12 +105,28 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// Blocking probe: the warp is suspended by the hardware until the phase completes or a time limit (here ~1 us) passes.
+__device__ __forceinline__ bool mbar_try_block(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000u) : "memory");
+    return ok != 0;
+}
+__device__ int g_tc_wait_mode;        // experiment switch: 0 = test_wait + nanosleep, 1 = try_wait (hardware suspend)
 // Wait with a fixed sleep between probes.  Polling costs issue slots and shared-memory pipeline slots that the
 // working warps need, so roles that wait for long events (epilogue, sorter) pass a long sleep.
 template <int kSleepNs = 200>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
     uint32_t tries = 0;
+    if (g_tc_wait_mode == 1) {
+        while (!mbar_try_block(bar, parity))
+            if (++tries > kSpinLimit / 8) __trap();
+        return;
+    }
     while (!mbar_try(bar, parity)) {
         __nanosleep(kSleepNs);
         if (++tries > kSpinLimit) __trap();   // a stuck pipeline traps instead of hanging the GPU
@@ -122,6 +146,8 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -155,14 +181,20 @@ __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[tmem] . B[smem descriptor]^T, kind::tf32, issued by one thread
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok));
+    return ok != 0;
+}
+// D[tmem] (+)= A[tmem] . B[smem descriptor]^T, kind::tf32, issued by one thread; ACC = 0 overwrites D
+template <int ACC>
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "n"(ACC) : "memory");
 }
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -319,7 +351,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             mbar_init(acc_full(i), 1);
             mbar_init(acc_empty(i), 128);
             mbar_init(sort_ready(i), 64);
-            mbar_init(sort_free(i), kTcSumWarps);
+            mbar_init(sort_free(i), 4 * (NB < kTcSumGroups ? NB : kTcSumGroups));   // the summer warps that have chunks
         }
         mbar_init(btab_bar, 1);
         fence_barrier_init();
@@ -354,8 +386,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         const unsigned rem = HWu - pix0;
         npx = rem < (unsigned)kTilePixels ? (int)rem : kTilePixels;
     };
+    // Each warpgroup first takes its share of the register file (the releases let the requests through).
     if (warp < kTcConvWarps) {
         // =========================== converters ========================================
+        reg_inc<kTcRegsConv>();
         const int quarter = warp & 3, group = warp >> 2;
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
         const uint32_t lane_word = 4u * (uint32_t)(32 * quarter + lane);
@@ -363,8 +397,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         uint32_t rphase = 0;
         int t = 0, blk = group;
         float x[kTcChunkC];
-        for (int q = group; q < total_chunks; q += 2) {
-            if (blk >= NB) { blk -= NB; ++t; }
+        for (int q = group; q < total_chunks; q += kTcConvGroups) {
+            while (blk >= NB) { blk -= NB; ++t; }
             const int par = t & 1;
             const int as = q & (kTcAStages - 1);
             const uint32_t use = (uint32_t)q >> 2;
@@ -376,7 +410,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(ring_empty(stage));      // this warp's reads of the stage are issued and ordered before the arrive
-            stage += 2;
+            stage += kTcConvGroups;
             if (stage >= nstage) { stage -= nstage; rphase ^= 1; }
             if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[1]);   // partial columns [par] of tile t-2 consumed
             mbar_wait_t<64>(empty_a(as), (use & 1) ^ 1, prof, dbg[2]);
@@ -417,10 +451,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             tc_fence_before();
             mbar_arrive(full_a(as));
             if (prof) dbg[3] += clock64() - t_cv0;         // centring / splitting / tcgen05.st / wait::st
-            blk += 2;
+            blk += kTcConvGroups;
         }
-    } else if (SUMS && warp < kTcSumWarp0 + kTcSumWarps) {
+    } else if (warp < kTcSumWarp0 + kTcSumWarps) {
         // =========================== summers ===========================================
+        reg_dec<kTcRegsSum>();
+        if (SUMS) {
         // Class sums of the chunk's 32 channels (lane = channel), read straight from the ring stage.  The class-sorted
         // pixels of the tile are cut into four ranges of 32 entries, one per warp of the group: balanced whatever the
         // label map looks like.  The pixel offsets of the entries come four at a time from warp-uniform (broadcast)
@@ -430,16 +466,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         // just marks those entries -- which the warp that started the class adds to the class row after the group's
         // barrier, heads in range order.  One writer per accumulator at a time, fixed order, no atomics.
         const int sw = warp - kTcSumWarp0;
-        const int quarter = sw & 3, group = sw >> 2;        // quarter = which 32 sorted entries; group g takes chunks g, g+2, ..
+        const int quarter = sw & 3, group = sw >> 2;        // quarter = which 32 sorted entries; group g takes chunks g, g+4, .. of a tile
         const int gbar = 3 + group;                         // named barrier of the group (128 threads)
-        int stage = group;
+        int stage = 0, qprev = 0;
         uint32_t rphase = 0;
-        int t = 0, blk = group;
         int hp = 0;                                         // head buffer of this chunk (alternates over the group's chunks)
         const uint32_t lane_off = (uint32_t)ring_slot(lane) * kTcRowBytes + 4u * (uint32_t)maps.shift[lane & 3];   // pixel 0 of this lane's channel row
         const int idx = 32 * quarter + lane;                // this warp's range: entries 32*quarter .. +31
-        for (int q = group; q < total_chunks; q += 2, hp ^= 1) {
-            if (blk >= NB) { blk -= NB; ++t; }
+        const bool single = group + kTcSumGroups >= NB;     // one chunk per tile: consecutive chunks of the group share their accumulator rows
+        for (int t = 0; t < my_tiles; ++t)
+        for (int blk = group; blk < NB; blk += kTcSumGroups, hp ^= 1) {
+            {   // ring stage of chunk q = t * NB + blk
+                const int q = t * NB + blk;
+                stage += q - qprev;
+                qprev = q;
+                while (stage >= nstage) { stage -= nstage; rphase ^= 1; }
+            }
             const int par = t & 1;
             mbar_wait_t<64>(sort_ready(par), ((uint32_t)t >> 1) & 1, prof, dbg[1]);
             mbar_wait_t<64>(ring_full(stage), rphase, prof, dbg[0]);
@@ -461,8 +503,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             uint32_t cur = a1 + (uint32_t)__shfl_sync(0xffffffffu, myrow, 0);
             float c1 = lds32(cur), c2 = lds32(cur + 128u);
             float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {            // 16 entries at a time: all their loads in flight at once
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {            // 16 entries at a time: all their loads in flight at once (kept rolled: code size)
                 if (16 * h >= nlive) continue;
                 int4 ov[4];
 #pragma unroll
@@ -480,20 +522,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                     __syncwarp();
                     if (lane == 0) mbar_arrive(ring_empty(stage));
                 }
+                // four entries at a time: without a segment end among the first three, the quad is a small tree (short
+                // dependent chains, one test); otherwise entry by entry.  Either way the order of the additions is a
+                // function of the sorted list alone.
+                const unsigned hb = endbits >> (16 * h);
+                auto flush = [&](int e) {            // entry e (0..15 of this half) ends a segment
+                    sts32(cur, c1 + s1);
+                    sts32(cur + 128u, c2 + s2);
+                    s1 = 0.f;
+                    s2 = 0.f;
+                    if (16 * h + e < 31) {           // the next segment's accumulators
+                        cur = a1 + (uint32_t)__shfl_sync(0xffffffffu, myrow, 16 * h + e + 1);
+                        c1 = lds32(cur);
+                        c2 = lds32(cur + 128u);
+                    }
+                };
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    s1 += xv[e];
-                    s2 = fmaf(xv[e], xv[e], s2);
-                    if (endbits & (1u << (16 * h + e))) {
-                        sts32(cur, c1 + s1);
-                        sts32(cur + 128u, c2 + s2);
-                        s1 = 0.f;
-                        s2 = 0.f;
-                        if (16 * h + e < 31) {       // the next segment's accumulators
-                            cur = a1 + (uint32_t)__shfl_sync(0xffffffffu, myrow, 16 * h + e + 1);
-                            c1 = lds32(cur);
-                            c2 = lds32(cur + 128u);
-                        }
+                for (int qd = 0; qd < 4; ++qd) {
+                    const float x0 = xv[4 * qd], x1 = xv[4 * qd + 1], x2 = xv[4 * qd + 2], x3 = xv[4 * qd + 3];
+                    const unsigned qb = (hb >> (4 * qd)) & 0xfu;
+                    if ((qb & 7u) == 0u) {
+                        s1 += (x0 + x1) + (x2 + x3);
+                        s2 += fmaf(x1, x1, x0 * x0) + fmaf(x3, x3, x2 * x2);
+                        if (qb & 8u) flush(4 * qd + 3);
+                    } else {
+                        s1 += x0; s2 = fmaf(x0, x0, s2);
+                        if (qb & 1u) flush(4 * qd);
+                        s1 += x1; s2 = fmaf(x1, x1, s2);
+                        if (qb & 2u) flush(4 * qd + 1);
+                        s1 += x2; s2 = fmaf(x2, x2, s2);
+                        if (qb & 4u) flush(4 * qd + 2);
+                        s1 += x3; s2 = fmaf(x3, x3, s2);
+                        if (qb & 8u) flush(4 * qd + 3);
                     }
                 }
             }
@@ -501,8 +561,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ring_empty(stage));
             }
-            stage += 2;
-            if (stage >= nstage) { stage -= nstage; rphase ^= 1; }
             if (prof) dbg[3] += clock64() - t_seg0;
             named_bar_sync(gbar, 128);          // all heads of this chunk are complete
             {   // move the heads of the classes this warp started into their class rows
@@ -520,81 +578,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 }
             }
             // The head rows alternate between two buffers, so the next chunk's heads cannot meet this chunk's moves; the
-            // class rows of a chunk are revisited NB/2 chunks later, behind at least one more group barrier -- except when
-            // the group owns a single chunk per tile (NB == 2): then the next chunk flushes into the very same rows.
-            if (NB == 2) named_bar_sync(gbar, 128);
-            blk += 2;
-            if (blk >= NB) {                    // that was this group's last chunk of the tile
+            // class rows of a chunk are revisited two chunks later, behind one more group barrier -- except when the
+            // group owns a single chunk per tile: then the next chunk flushes into the very same rows.
+            if (single) named_bar_sync(gbar, 128);
+            if (blk + kTcSumGroups >= NB) {     // that was this group's last chunk of the tile
                 if (lane == 0) mbar_arrive(sort_free(par));
             }
         }
-    } else if (warp == kTcMmaWarp) {
-        // =========================== MMA issuer ========================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(128, 32);
-            const uint32_t bhi_addr = smem_u32(Bhi), blo_addr = smem_u32(Blo);
-            mbar_wait<32>(btab_bar, 0);             // the B tables have landed (bulk copies of the prologue)
-            int q = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                const int par = t & 1;
-                if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
-                tc_fence_after();
-                const uint32_t dcol = tmem_base + kAccCol0 + (uint32_t)par * 32;
-                for (int b = 0; b < NB; ++b, ++q) {
-                    const int as = q & (kTcAStages - 1);
-                    const uint32_t use = (uint32_t)q >> 2;
-                    mbar_wait_t<32>(full_a(as), use & 1, prof, dbg[1]);
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t a_hi = tmem_base + (uint32_t)as * 64 + ks * 8;
-                        const uint32_t a_lo = a_hi + 32;
-                        const uint32_t koff = (uint32_t)((b * kTcChunkC + ks * 8) / 4) * 512u;   // 4 channels = one 512-byte slab
-                        const uint64_t d_hi = make_bdesc(bhi_addr + koff, 512, 128);
-                        const uint64_t d_lo = make_bdesc(blo_addr + koff, 512, 128);
-                        tc_mma_tf32_ts(dcol, a_lo, d_lo, idesc, (b | ks) != 0);     // smallest terms first
-                        tc_mma_tf32_ts(dcol, a_lo, d_hi, idesc, 1);
-                        tc_mma_tf32_ts(dcol, a_hi, d_lo, idesc, 1);
-                        tc_mma_tf32_ts(dcol, a_hi, d_hi, idesc, 1);
-                    }
-                    tc_commit(empty_a(as));             // A stage reusable once these MMAs retire
-                }
-                tc_commit(acc_full(par));               // accumulator complete
-            }
-        }
-        __syncwarp();
-    } else if (warp == kTcProdWarp) {
-        // =========================== producer ===========================================
-        // One thread.  Chunk (tile, 32 channels from cb) = four tensor copies, one per channel residue r: box of 132
-        // floats x 8 channel groups starting at float index pix0 (a 16-byte aligned address; pixel pix0 lands shift_r
-        // floats into the row, indices past the row's end are zero-filled), channel group cb / 4, image img.
-        if (lane == 0) {
-            uint64_t policy;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-#pragma unroll
-            for (int r = 0; r < 4; ++r) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.map[r]) : "memory");
-            int stage = 0;
-            uint32_t rphase = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                unsigned img, pix0;
-                int npx;
-                tile_of(t, img, pix0, npx);
-                for (int b = 0; b < NB; ++b) {
-                    mbar_wait_t<64>(ring_empty(stage), rphase ^ 1, prof, dbg[0]);
-                    const uint32_t dst = ring + (uint32_t)stage * kTcStageBytes;
-                    const uint32_t bar = ring_full(stage);
-                    mbar_arrive_tx(bar, (uint32_t)kTcStageBytes);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        tma_load_3d(dst + (uint32_t)(8 * r) * kTcRowBytes, &maps.map[r], (int)pix0, (c_base + b * kTcChunkC) / 4,
-                                    (int)img, bar, policy);
-                    if (++stage == nstage) { stage = 0; rphase ^= 1; }
-                }
-            }
-        }
-        __syncwarp();
+        }   // SUMS
     } else if (warp >= kTcEpiWarp0 && warp < kTcEpiWarp0 + 4) {
         // =========================== epilogue ===========================================
+        reg_inc<kTcRegsEpi>();
         const int et = tid - kTcEpiWarp0 * 32;          // 0..127 = pixel row of the tile = TMEM lane
         const uint32_t lane_base = (uint32_t)(et & ~31) << 16;
         PixelStats st;
@@ -608,7 +602,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             float pri[CP];
             {   // prior row of this pixel: issued before the wait so its latency hides behind the MMAs
                 if (et < npx && p.prior != nullptr && (p.labels != nullptr || p.soft != nullptr)) {
-                    load_pixel_row<CP>(p.prior, C, HW, n0 + et, pri);
+                    load_pixel_row_at<CP>(p.prior + ((size_t)img * C) * HW + pix0 + et, C, HWu, pri);
                 } else {
 #pragma unroll
                     for (int k = 0; k < CP; ++k) pri[k] = 0.f;
@@ -648,6 +642,77 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 p.stat_partials[(size_t)blockIdx.x * kStatSlots + et] = xs;
             }
         }
+    } else {
+    // sorter, MMA issuer and producer share the last warpgroup, which keeps its 64 registers
+    if (warp == kTcMmaWarp) {
+        // =========================== MMA issuer ========================================
+        // The whole warp walks the loop (uniform control flow); one elected lane issues.  Descriptors are the chunk's
+        // base descriptor plus a constant per K-step (the address field counts 16-byte units; 8 channels = 64 units).
+        {
+            const uint32_t idesc = make_idesc_tf32(128, 32);
+            const uint64_t bhi0 = make_bdesc(smem_u32(Bhi), 512, 128), blo0 = make_bdesc(smem_u32(Blo), 512, 128);
+            mbar_wait<32>(btab_bar, 0);             // the B tables have landed (bulk copies of the prologue)
+            int q = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int par = t & 1;
+                if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
+                const uint32_t dcol = tmem_base + kAccCol0 + (uint32_t)par * 32;
+                for (int b = 0; b < NB; ++b, ++q) {
+                    const int as = q & (kTcAStages - 1);
+                    const uint32_t use = (uint32_t)q >> 2;
+                    mbar_wait_t<32>(full_a(as), use & 1, prof, dbg[1]);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_hi = tmem_base + (uint32_t)as * 64, a_lo = a_hi + 32;
+                        const uint64_t d_hi = bhi0 + (uint64_t)(b * 256), d_lo = blo0 + (uint64_t)(b * 256);
+                        // smallest terms first; the very first MMA of a tile overwrites the accumulator
+                        if (b == 0) tc_mma_tf32<0>(dcol, a_lo, d_hi, idesc);
+                        else tc_mma_tf32<1>(dcol, a_lo, d_hi, idesc);
+                        tc_mma_tf32<1>(dcol, a_hi, d_lo, idesc);
+                        tc_mma_tf32<1>(dcol, a_hi, d_hi, idesc);
+#pragma unroll
+                        for (int ks = 1; ks < 4; ++ks) {
+                            tc_mma_tf32<1>(dcol, a_lo + ks * 8, d_hi + ks * 64, idesc);
+                            tc_mma_tf32<1>(dcol, a_hi + ks * 8, d_lo + ks * 64, idesc);
+                            tc_mma_tf32<1>(dcol, a_hi + ks * 8, d_hi + ks * 64, idesc);
+                        }
+                        tc_commit(empty_a(as));             // A stage reusable once these MMAs retire
+                        if (b == NB - 1) tc_commit(acc_full(par));      // accumulator complete
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == kTcProdWarp) {
+        // =========================== producer ===========================================
+        // One thread.  Chunk (tile, 32 channels from cb) = four tensor copies, one per channel residue r: box of 132
+        // floats x 8 channel groups starting at float index pix0 (a 16-byte aligned address; pixel pix0 lands shift_r
+        // floats into the row, indices past the row's end are zero-filled), channel group cb / 4, image img.
+        if (lane == 0) {
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+#pragma unroll
+            for (int r = 0; r < 4; ++r) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.map[r]) : "memory");
+            int stage = 0;
+            uint32_t rphase = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                unsigned img, pix0;
+                int npx;
+                tile_of(t, img, pix0, npx);
+                for (int b = 0; b < NB; ++b) {
+                    mbar_wait_t<64>(ring_empty(stage), rphase ^ 1, prof, dbg[0]);
+                    const uint32_t dst = ring + (uint32_t)stage * kTcStageBytes;
+                    const uint32_t bar = ring_full(stage);
+                    mbar_arrive_tx(bar, (uint32_t)kTcStageBytes);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        tma_load_3d(dst + (uint32_t)(8 * r) * kTcRowBytes, &maps.map[r], (int)pix0, (c_base + b * kTcChunkC) / 4,
+                                    (int)img, bar, policy);
+                    if (++stage == nstage) { stage = 0; rphase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
     } else if (SUMS && warp >= kTcSortWarp0 && warp < kTcSortWarp0 + 2) {
         // =========================== sorter ================================================
         // Per tile: class of every pixel = first argmax of the EMA logits (prototype_handler.py:83-86), then a stable
@@ -662,11 +727,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             unsigned img, pix0;
             int npx;
             tile_of(t, img, pix0, npx);
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int m = 32 * (2 * sw + r) + lane;
-                if (m < npx) load_pixel_row<CP>(p.logits, C, HW, (long long)img * HW + pix0 + m, lv[r]);
-            }
+            const float* lp = p.logits + ((size_t)img * C) * HW + pix0 + 64 * sw + lane;
+            if (64 * sw + lane < npx) load_pixel_row_at<CP>(lp, C, HWu, lv[0]);
+            if (64 * sw + 32 + lane < npx) load_pixel_row_at<CP>(lp + 32, C, HWu, lv[1]);
         };
         fetch_logits(0);
         const unsigned lt_mask = (1u << lane) - 1u;
@@ -680,7 +743,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int v = 2 * sw + r;
-                y[r] = (32 * v + lane < npx) ? first_argmax<CP>(lv[r], C) : -1;
+                y[r] = (32 * v + lane < npx) ? first_argmax_fast<CP>(lv[r], C) : -1;
                 bucket[r] = y[r] < 0 ? 32 : y[r];
                 peers[r] = __match_any_sync(0xffffffffu, bucket[r]);
                 wc[v * 36 + lane] = 0;
@@ -736,6 +799,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             named_bar_sync(1, 64);                               // wc is reused by the next tile
         }
     }
+
+    }   // last warpgroup
 
     // ---- teardown: publish the class partials, release tensor memory
     if (PROF && p.debug != nullptr && lane == 0) {
@@ -830,6 +895,15 @@ static int launch_tc(FusedParams p, int grid, cudaStream_t stream) {
     if (smem > smem_set[dev]) {
         ONDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set[dev] = smem;
+    }
+    {   // experiment switch (ONDA_TC_WAIT)
+        static int mode_set = -1;
+        const char* e = getenv("ONDA_TC_WAIT");
+        const int mode = e ? atoi(e) : 1;
+        if (mode != mode_set) {
+            ONDA_CUDA_TRY(cudaMemcpyToSymbol(g_tc_wait_mode, &mode, sizeof(int)));
+            mode_set = mode;
+        }
     }
     TcMaps maps;
     const int rc = tc_make_maps(p.feat, p.B, p.D, p.HW, &maps);

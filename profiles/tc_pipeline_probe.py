@@ -22,10 +22,10 @@ lib.onda_debug_set_buffer(None)
 d = buf.view(148, 32, 8).double().cpu()
 tot = d[:, :, 7]
 names = {"converter": (0, 8, ["wait ring_full", "wait acc_empty", "wait empty_a(mma)", "convert + tcgen05.st + wait::st"]),
-         "summer": (8, 16, ["wait ring_full", "wait sort_ready", "-", "class-sum loop"]),
-         "epilogue": (16, 20, ["wait acc_full"]), "sorter": (20, 22, ["wait sort_free"]),
-         "mma": (22, 23, ["wait acc_empty", "wait full_a"]), "producer": (23, 24, ["wait ring_empty"])}
-print("mean total cycles per warp:", tot[:, :24].mean().item())
+         "summer": (8, 24, ["wait ring_full", "wait sort_ready", "-", "class-sum loop"]),
+         "epilogue": (24, 28, ["wait acc_full"]), "sorter": (28, 30, ["wait sort_free"]),
+         "mma": (30, 31, ["wait acc_empty", "wait full_a"]), "producer": (31, 32, ["wait ring_empty"])}
+print("mean total cycles per warp:", tot[:, :32].mean().item())
 for role, (a, b, labels) in names.items():
     t = tot[:, a:b].mean().item()
     print(f"{role:9s} total {t:10.0f} cyc")
