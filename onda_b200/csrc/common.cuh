@@ -44,25 +44,28 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 
 // Distance-table layout (floats), built by onda_build_distance_table:
 //   sigma[Dp] | w[Dp] | mu[Dp] | bias[32] | Q[Dp][CP]  (channel-major, CP = padded_classes(C))
-//   | Bhi[Dp/4][32][4] | Blo[Dp/4][32][4]   TF32 split of -2*Q laid out as the tcgen05 B operand:
+//   | Bhi[Dp/4][BR][4] | Blo[Dp/4][BR][4]   TF32 split of -2*Q laid out as the tcgen05 B operand:
 //     K-major, no swizzle, 8x16-byte core matrices: element (class n, channel c) sits at float index
-//     (c/4)*128 + n*4 + (c%4), so LBO (next 4 channels) = 512 B and SBO (next 8 classes) = 128 B.
+//     (c/4)*4*BR + n*4 + (c%4), so LBO (next 4 channels) = 16*BR bytes and SBO (next 8 classes) = 128 B.
+//     BR = 24 rows when C <= 24 (else 32): the MMA is 32 classes wide, so its last class group then reads the
+//     first group of the next 4-channel slab -- accumulator columns 24..31 hold garbage nobody reads -- and the
+//     tables are a quarter smaller (one more stage of the feature ring fits in shared memory).
 // Dp = D rounded up to 32; padded channels carry w = 0, Q = 0 so they contribute nothing.
 struct TableLayout {
-    int C, D, Dp, CP;
+    int C, D, Dp, CP, BR;
     size_t off_sigma, off_w, off_mu, off_bias, off_q, off_qhi, off_qlo, off_scratch, total;
 };
 __host__ __device__ inline TableLayout table_layout(int C, int D) {
     TableLayout t;
-    t.C = C; t.D = D; t.Dp = round_up(D, 32); t.CP = padded_classes(C);
+    t.C = C; t.D = D; t.Dp = round_up(D, 32); t.CP = padded_classes(C); t.BR = C <= 24 ? 24 : 32;
     t.off_sigma = 0;
     t.off_w = t.off_sigma + t.Dp;
     t.off_mu = t.off_w + t.Dp;
     t.off_bias = t.off_mu + t.Dp;
     t.off_q = t.off_bias + 32;
     t.off_qhi = t.off_q + (size_t)t.Dp * t.CP;
-    t.off_qlo = t.off_qhi + (size_t)32 * t.Dp;
-    t.off_scratch = t.off_qlo + (size_t)32 * t.Dp;          // per-CTA bias partials (doubles) + ticket of the table kernel
+    t.off_qlo = t.off_qhi + (size_t)t.BR * t.Dp + 32;            // + 32: the over-read of the last slab stays inside the table
+    t.off_scratch = t.off_qlo + (size_t)t.BR * t.Dp + 32;        // per-CTA bias partials (doubles) + ticket of the table kernel
     t.total = t.off_scratch + (size_t)2 * 32 * (t.Dp / 32) + 8;
     return t;
 }

@@ -78,7 +78,9 @@ constexpr int kTcStageBytes = kTcChunkC * kTcRowBytes;
 constexpr int kTcMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = kTcAStages * 64;   // accumulators after the A stages
-constexpr uint32_t kApartCol0 = kAccCol0 + 64;   // then sum_j w_j x'_j^2 of each chunk: 2 tile parities x 8 chunks, lane = pixel
+constexpr uint32_t kAccSet = 96;                 // per tile parity: three accumulators of 32 columns (one per term of the split, so
+                                                 // that consecutive MMAs do not wait for each other's accumulator)
+constexpr uint32_t kApartCol0 = kAccCol0 + 2 * kAccSet;   // then sum_j w_j x'_j^2 of each chunk: 2 tile parities x 8 chunks, lane = pixel
 constexpr int kTcHeadFloats = kTcSumGroups * 2 * 3 * kTcChunkC;   // per statistic: head partials of ranges 1..3 of every group's current chunk, double-buffered over the group's chunks
 constexpr uint32_t kSpinLimit = 20000000u;       // failed probes (each followed by a sleep) before giving up
 
@@ -208,6 +210,29 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]);
+// the first CP (20 or 32) columns of an accumulator
+template <int CP>
+__device__ __forceinline__ void tc_ld_cols(uint32_t taddr, uint32_t (&v)[CP]) {
+    if constexpr (CP == 32) {
+        tc_ld32(taddr, v);
+    } else {
+        static_assert(CP == 20, "padded class count is 20 or 32");
+        tc_ld16(taddr, v);
+        tc_ld4(taddr + 16, v + 16);
+    }
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -251,6 +276,7 @@ struct TcSmem {
     int nstage;
 };
 __host__ __device__ inline TcSmem tc_smem(int Dc, int C, int CP, bool sums, int nstage) {
+    const int BR = C <= 24 ? 24 : 32;        // rows of the B tables (TableLayout::BR)
     // Everything whose size does not depend on D or C comes first: its addresses are compile-time offsets from the
     // shared-memory base and cost no registers.
     TcSmem s;
@@ -267,8 +293,8 @@ __host__ __device__ inline TcSmem tc_smem(int Dc, int C, int CP, bool sums, int 
     o = (o + 127) / 128 * 128;
     s.mu = o; o += (size_t)Dc * 4;
     s.w = o; o += (size_t)Dc * 4;
-    s.bhi = o; o += (size_t)32 * Dc * 4;
-    s.blo = o; o += (size_t)32 * Dc * 4;
+    s.bhi = o; o += (size_t)BR * Dc * 4;
+    s.blo = o; o += (size_t)BR * Dc * 4;
     s.acc = o; o += sums ? (size_t)2 * (C * Dc + kTcHeadFloats) * 4 : 0;   // [class * Dc/32 + chunk | then 3 heads per group][sum | sum of squares][32 channels]
     o = (o + 127) / 128 * 128;
     s.ring = o; o += (size_t)nstage * kTcStageBytes;
@@ -357,10 +383,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         fence_barrier_init();
         // B operand tables (hi, lo) of this CTA's channel slice: two bulk asynchronous copies, off everybody's
         // critical path -- only the MMA issuer waits for them, before its first MMA
-        const uint32_t bytes = (uint32_t)(32 * Dc) * 4u;
+        const uint32_t bytes = (uint32_t)(T.BR * Dc) * 4u;
         mbar_arrive_tx(btab_bar, 2u * bytes);
-        bulk_g2s_plain(smem_u32(Bhi), p.table + T.off_qhi + (size_t)c_base * 32, bytes, btab_bar);
-        bulk_g2s_plain(smem_u32(Blo), p.table + T.off_qlo + (size_t)c_base * 32, bytes, btab_bar);
+        bulk_g2s_plain(smem_u32(Bhi), p.table + T.off_qhi + (size_t)c_base * T.BR, bytes, btab_bar);
+        bulk_g2s_plain(smem_u32(Blo), p.table + T.off_qlo + (size_t)c_base * T.BR, bytes, btab_bar);
     }
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
@@ -420,7 +446,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const uint32_t tcol = tmem_base + lane_base + (uint32_t)as * 64;
             const ulonglong2* mu4 = reinterpret_cast<const ulonglong2*>(mus + blk * kTcChunkC);     // -mu, two pairs per load
             const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(wsm + blk * kTcChunkC);
-            const uint64_t neg1 = pack2(-1.f, -1.f);
+            const uint64_t neg1 = pack2(-1.f, -1.f), vk = pack2(8193.f, 8193.f);
 #pragma unroll
             for (int part = 0; part < 4; ++part) {       // eight channels at a time: bounds the live registers
                 uint32_t hi[8], lo[8];
@@ -433,11 +459,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                         const int j = j4 * 4 + 2 * e;
                         const uint64_t xc = fadd2(pack2(x[part * 8 + j], x[part * 8 + j + 1]), mm[e]);
                         a2 = ffma2(fmul2(xc, xc), ww[e], a2);
-                        const uint32_t h0 = ((uint32_t)xc + 0x1000u) & 0xffffe000u;            // round to TF32 (10-bit mantissa)
-                        const uint32_t h1 = ((uint32_t)(xc >> 32) + 0x1000u) & 0xffffe000u;
-                        const uint64_t l2 = ffma2((uint64_t)h0 | ((uint64_t)h1 << 32), neg1, xc);     // exact remainder
-                        hi[j] = h0;
-                        hi[j + 1] = h1;
+                        // Veltkamp split: hi = x' rounded to 11 significant bits (a TF32 value), lo = the exact remainder
+                        const uint64_t cc = fmul2(xc, vk);                 // x' * (2^13 + 1)
+                        const uint64_t h2 = ffma2(ffma2(xc, neg1, cc), neg1, cc);      // cc - (cc - x')
+                        const uint64_t l2 = ffma2(h2, neg1, xc);
+                        hi[j] = (uint32_t)h2;
+                        hi[j + 1] = (uint32_t)(h2 >> 32);
                         lo[j] = (uint32_t)l2;
                         lo[j + 1] = (uint32_t)(l2 >> 32);
                     }
@@ -542,8 +569,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                     const float x0 = xv[4 * qd], x1 = xv[4 * qd + 1], x2 = xv[4 * qd + 2], x3 = xv[4 * qd + 3];
                     const unsigned qb = (hb >> (4 * qd)) & 0xfu;
                     if ((qb & 7u) == 0u) {
-                        s1 += (x0 + x1) + (x2 + x3);
-                        s2 += fmaf(x1, x1, x0 * x0) + fmaf(x3, x3, x2 * x2);
+                        const uint64_t p01 = pack2(x0, x1), p23 = pack2(x2, x3);
+                        const uint64_t t1 = fadd2(p01, p23), t2 = ffma2(p23, p23, fmul2(p01, p01));
+                        s1 += __uint_as_float((uint32_t)t1) + __uint_as_float((uint32_t)(t1 >> 32));
+                        s2 += __uint_as_float((uint32_t)t2) + __uint_as_float((uint32_t)(t2 >> 32));
                         if (qb & 8u) flush(4 * qd + 3);
                     } else {
                         s1 += x0; s2 = fmaf(x0, x0, s2);
@@ -610,8 +639,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             }
             mbar_wait_t<400>(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
             tc_fence_after();
-            uint32_t dv[32];
-            tc_ld32(tmem_base + lane_base + kAccCol0 + (uint32_t)par * 32, dv);
+            // the three accumulators of the split (hi.hi | hi.lo | lo.hi): small terms first
+            const uint32_t dcol = tmem_base + lane_base + kAccCol0 + (uint32_t)par * kAccSet;
+            float d2[CP];
+            {
+                uint32_t u[CP], v[CP];
+                tc_ld_cols<CP>(dcol + 32, u);
+                tc_ld_cols<CP>(dcol + 64, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int k = 0; k < CP; ++k) d2[k] = __uint_as_float(u[k]) + __uint_as_float(v[k]);
+            }
+            uint32_t dv[CP];
+            tc_ld_cols<CP>(dcol, dv);
             uint32_t av[8];
             tc_ld8(tmem_base + lane_base + kApartCol0 + (uint32_t)par * 8, av);
             tc_wait_ld();
@@ -620,9 +660,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             for (int b = 0; b < 8; ++b) a_tot += b < NB ? __uint_as_float(av[b]) : 0.f;
             tc_fence_before();
             mbar_arrive(acc_empty(par));
-            float d2[CP];
 #pragma unroll
-            for (int k = 0; k < CP; ++k) d2[k] = (a_tot + __ldg(bias + k)) + __uint_as_float(dv[k]);
+            for (int k = 0; k < CP; ++k) d2[k] = (a_tot + __ldg(bias + k)) + (d2[k] + __uint_as_float(dv[k]));
             finish_pixel_rows<CP, WANT_DIST>(p, C, d2, n0, npx, et, out_stage, st, pri);
         }
         // fixed-order reduction of the statistics over the four epilogue warps
@@ -650,13 +689,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         // base descriptor plus a constant per K-step (the address field counts 16-byte units; 8 channels = 64 units).
         {
             const uint32_t idesc = make_idesc_tf32(128, 32);
-            const uint64_t bhi0 = make_bdesc(smem_u32(Bhi), 512, 128), blo0 = make_bdesc(smem_u32(Blo), 512, 128);
+            const uint32_t lbo = 16u * (uint32_t)T.BR;       // bytes between 4-channel slabs of the B tables
+            const uint64_t bhi0 = make_bdesc(smem_u32(Bhi), lbo, 128), blo0 = make_bdesc(smem_u32(Blo), lbo, 128);
+            const uint32_t kstep = 2u * (uint32_t)T.BR;      // one K-step = 8 channels = two slabs, in the descriptor's 16-byte units
             mbar_wait<32>(btab_bar, 0);             // the B tables have landed (bulk copies of the prologue)
             int q = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 const int par = t & 1;
                 if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
-                const uint32_t dcol = tmem_base + kAccCol0 + (uint32_t)par * 32;
+                const uint32_t d0 = tmem_base + kAccCol0 + (uint32_t)par * kAccSet, d1 = d0 + 32, d2 = d0 + 64;
                 for (int b = 0; b < NB; ++b, ++q) {
                     const int as = q & (kTcAStages - 1);
                     const uint32_t use = (uint32_t)q >> 2;
@@ -664,17 +705,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_hi = tmem_base + (uint32_t)as * 64, a_lo = a_hi + 32;
-                        const uint64_t d_hi = bhi0 + (uint64_t)(b * 256), d_lo = blo0 + (uint64_t)(b * 256);
-                        // smallest terms first; the very first MMA of a tile overwrites the accumulator
-                        if (b == 0) tc_mma_tf32<0>(dcol, a_lo, d_hi, idesc);
-                        else tc_mma_tf32<1>(dcol, a_lo, d_hi, idesc);
-                        tc_mma_tf32<1>(dcol, a_hi, d_lo, idesc);
-                        tc_mma_tf32<1>(dcol, a_hi, d_hi, idesc);
+                        const uint64_t d_hi = bhi0 + (uint64_t)((uint32_t)b * 4u * kstep), d_lo = blo0 + (uint64_t)((uint32_t)b * 4u * kstep);
+                        // term i of the split accumulates in its own columns; the first MMAs of a tile overwrite them
+                        if (b == 0) {
+                            tc_mma_tf32<0>(d0, a_hi, d_hi, idesc);
+                            tc_mma_tf32<0>(d1, a_hi, d_lo, idesc);
+                            tc_mma_tf32<0>(d2, a_lo, d_hi, idesc);
+                        } else {
+                            tc_mma_tf32<1>(d0, a_hi, d_hi, idesc);
+                            tc_mma_tf32<1>(d1, a_hi, d_lo, idesc);
+                            tc_mma_tf32<1>(d2, a_lo, d_hi, idesc);
+                        }
 #pragma unroll
                         for (int ks = 1; ks < 4; ++ks) {
-                            tc_mma_tf32<1>(dcol, a_lo + ks * 8, d_hi + ks * 64, idesc);
-                            tc_mma_tf32<1>(dcol, a_hi + ks * 8, d_lo + ks * 64, idesc);
-                            tc_mma_tf32<1>(dcol, a_hi + ks * 8, d_hi + ks * 64, idesc);
+                            tc_mma_tf32<1>(d0, a_hi + ks * 8, d_hi + (uint64_t)(ks * kstep), idesc);
+                            tc_mma_tf32<1>(d1, a_hi + ks * 8, d_lo + (uint64_t)(ks * kstep), idesc);
+                            tc_mma_tf32<1>(d2, a_lo + ks * 8, d_hi + (uint64_t)(ks * kstep), idesc);
                         }
                         tc_commit(empty_a(as));             // A stage reusable once these MMAs retire
                         if (b == NB - 1) tc_commit(acc_full(par));      // accumulator complete
