@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
             // (both parts rounded to nearest TF32 here: the tensor core would truncate the low 13 bits)
             const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
             if (k < T.BR) {
-                const size_t bi = (size_t)(j >> 2) * (4 * T.BR) + (size_t)k * 4 + (j & 3);
-                table[T.off_qhi + bi] = hi;
-                table[T.off_qlo + bi] = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);
+                const size_t bi = (size_t)(j >> 2) * (8 * T.BR) + (size_t)k * 4 + (j & 3);
+                table[T.off_b + bi] = hi;
+                table[T.off_b + bi + 4 * T.BR] = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);
             }
         }
 #pragma unroll

@@ -44,16 +44,16 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 
 // Distance-table layout (floats), built by onda_build_distance_table:
 //   sigma[Dp] | w[Dp] | mu[Dp] | bias[32] | Q[Dp][CP]  (channel-major, CP = padded_classes(C))
-//   | Bhi[Dp/4][BR][4] | Blo[Dp/4][BR][4]   TF32 split of -2*Q laid out as the tcgen05 B operand:
-//     K-major, no swizzle, 8x16-byte core matrices: element (class n, channel c) sits at float index
-//     (c/4)*4*BR + n*4 + (c%4), so LBO (next 4 channels) = 16*BR bytes and SBO (next 8 classes) = 128 B.
-//     BR = 24 rows when C <= 24 (else 32): the MMA is 32 classes wide, so its last class group then reads the
-//     first group of the next 4-channel slab -- accumulator columns 24..31 hold garbage nobody reads -- and the
-//     tables are a quarter smaller (one more stage of the feature ring fits in shared memory).
+//   | B[Dp/4][2*BR][4]   TF32 split of -2*Q laid out as the tcgen05 B operand: K-major, no swizzle, 8x16-byte
+//     core matrices.  Per 4-channel slab: BR rows of hi parts, then BR rows of lo parts; element (class n, channel c)
+//     of part s (0 = hi, 1 = lo) sits at float index (c/4)*8*BR + (s*BR + n)*4 + (c%4), so LBO (next 4 channels) =
+//     32*BR bytes and SBO (next 8 classes) = 128 B.  BR = 24 rows when C <= 24 (else 32).  One 64-class-wide MMA on
+//     a slab start therefore yields hi.hi in accumulator columns 0..BR-1 and hi.lo in columns BR..2*BR-1 (the rest
+//     of its 64 columns is the next slab's beginning: garbage nobody reads), and a 32-wide MMA yields lo.hi.
 // Dp = D rounded up to 32; padded channels carry w = 0, Q = 0 so they contribute nothing.
 struct TableLayout {
     int C, D, Dp, CP, BR;
-    size_t off_sigma, off_w, off_mu, off_bias, off_q, off_qhi, off_qlo, off_scratch, total;
+    size_t off_sigma, off_w, off_mu, off_bias, off_q, off_b, off_scratch, total;
 };
 __host__ __device__ inline TableLayout table_layout(int C, int D) {
     TableLayout t;
@@ -63,9 +63,8 @@ __host__ __device__ inline TableLayout table_layout(int C, int D) {
     t.off_mu = t.off_w + t.Dp;
     t.off_bias = t.off_mu + t.Dp;
     t.off_q = t.off_bias + 32;
-    t.off_qhi = t.off_q + (size_t)t.Dp * t.CP;
-    t.off_qlo = t.off_qhi + (size_t)t.BR * t.Dp + 32;            // + 32: the over-read of the last slab stays inside the table
-    t.off_scratch = t.off_qlo + (size_t)t.BR * t.Dp + 32;        // per-CTA bias partials (doubles) + ticket of the table kernel
+    t.off_b = t.off_q + (size_t)t.Dp * t.CP;
+    t.off_scratch = t.off_b + (size_t)2 * t.BR * t.Dp + 64;      // (+ 64: the over-read of the last slab stays inside the table); per-CTA bias partials (doubles) + ticket of the table kernel
     t.total = t.off_scratch + (size_t)2 * 32 * (t.Dp / 32) + 8;
     return t;
 }

@@ -41,15 +41,14 @@
 //                statistics.
 //   warps 28-29  sorter: per tile, class of every pixel (first argmax of the EMA logits) and a stable
 //                counting sort of the 128 pixels by class, published for the summers (double-buffered).
-//   warp   30    MMA issuer: per chunk 4 K-steps x 3 tcgen05.mma (kind::tf32, M=128, N=32, K=8),
-//                A from TMEM, B = TF32 split of -2*w*(P-mu) resident in shared memory (bulk copies in the
-//                prologue that only this warp waits for).
+//   warp   30    MMA issuer: per chunk 4 K-steps x 2 tcgen05.mma (kind::tf32, M=128, K=8): hi(x') against the hi and
+//                lo rows of B at once (N=64) and lo(x') against the hi rows (N=32); A from TMEM (an MMA this narrow
+//                is bound by reading A, so the two hi terms share one read), B = TF32 split of -2*w*(P-mu) resident
+//                in shared memory (one bulk copy in the prologue that only this warp waits for).
 // The register file is re-split after the prologue (setmaxnreg): converters 72, summers 56, epilogue 80, the rest 64.
 // Every mbarrier has one producer side and one consumer side that visit it phase by phase, in order.
 // Two accumulator buffers of 32 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
 #include <cuda.h>
-
-#include <stdlib.h>
 
 #include <mutex>
 #include <utility>
@@ -82,7 +81,7 @@ constexpr uint32_t kAccSet = 96;                 // per tile parity: three accum
                                                  // that consecutive MMAs do not wait for each other's accumulator)
 constexpr uint32_t kApartCol0 = kAccCol0 + 2 * kAccSet;   // then sum_j w_j x'_j^2 of each chunk: 2 tile parities x 8 chunks, lane = pixel
 constexpr int kTcHeadFloats = kTcSumGroups * 2 * 3 * kTcChunkC;   // per statistic: head partials of ranges 1..3 of every group's current chunk, double-buffered over the group's chunks
-constexpr uint32_t kSpinLimit = 20000000u;       // failed probes (each followed by a sleep) before giving up
+constexpr uint32_t kSpinLimit = 4000000u;        // failed probes (each up to ~1 us of hardware suspension) before giving up
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,19 +95,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// One non-blocking probe of an mbarrier phase (test_wait: try_wait may park in the shared-memory pipeline
-// for a hardware time-out, and ~20 parked waiters starve the LDS/STS of the working warps).
+// One probe of an mbarrier phase; the hardware may suspend the warp until the phase completes or a time limit passes.
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Blocking probe: the warp is suspended by the hardware until the phase completes or a time limit (here ~1 us) passes.
-__device__ __forceinline__ bool mbar_try_block(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -117,29 +105,19 @@ __device__ __forceinline__ bool mbar_try_block(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000u) : "memory");
     return ok != 0;
 }
-__device__ int g_tc_wait_mode;        // experiment switch: 0 = test_wait + nanosleep, 1 = try_wait (hardware suspend)
-// Wait with a fixed sleep between probes.  Polling costs issue slots and shared-memory pipeline slots that the
-// working warps need, so roles that wait for long events (epilogue, sorter) pass a long sleep.
-template <int kSleepNs = 200>
+// Wait for a phase.  Every wake-up costs issue slots the working warps need (and any mbarrier event of the CTA
+// wakes a suspended warp), so inside a group of warps only ONE warp waits on the mbarrier and the others sleep in
+// the group's named barrier -- see the call sites.  A stuck pipeline traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try(bar, parity)) return;
     uint32_t tries = 0;
-    if (g_tc_wait_mode == 1) {
-        while (!mbar_try_block(bar, parity))
-            if (++tries > kSpinLimit / 8) __trap();
-        return;
-    }
-    while (!mbar_try(bar, parity)) {
-        __nanosleep(kSleepNs);
-        if (++tries > kSpinLimit) __trap();   // a stuck pipeline traps instead of hanging the GPU
-    }
+    while (!mbar_try(bar, parity))
+        if (++tries > kSpinLimit) __trap();
 }
 // wait that adds its duration to a diagnostic counter when profiling is on
-template <int kSleepNs = 200>
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, long long& acc_cycles) {
-    if (!prof) { mbar_wait<kSleepNs>(bar, parity); return; }
+    if (!prof) { mbar_wait(bar, parity); return; }
     const long long t0 = clock64();
-    mbar_wait<kSleepNs>(bar, parity);
+    mbar_wait(bar, parity);
     acc_cycles += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -272,7 +250,7 @@ __host__ __device__ constexpr int ring_slot(int j) { return 8 * (j & 3) + (j >> 
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------
 struct TcSmem {
-    size_t bars, tmem_ptr, eoff, ecls, cuts, wc, cnt, red, out, mu, w, bhi, blo, acc, ring, total;  // byte offsets
+    size_t bars, tmem_ptr, eoff, ecls, cuts, wc, cnt, red, out, mu, w, btab, acc, ring, total;  // byte offsets
     int nstage;
 };
 __host__ __device__ inline TcSmem tc_smem(int Dc, int C, int CP, bool sums, int nstage) {
@@ -293,8 +271,7 @@ __host__ __device__ inline TcSmem tc_smem(int Dc, int C, int CP, bool sums, int 
     o = (o + 127) / 128 * 128;
     s.mu = o; o += (size_t)Dc * 4;
     s.w = o; o += (size_t)Dc * 4;
-    s.bhi = o; o += (size_t)BR * Dc * 4;
-    s.blo = o; o += (size_t)BR * Dc * 4;
+    s.btab = o; o += (size_t)2 * BR * Dc * 4;
     s.acc = o; o += sums ? (size_t)2 * (C * Dc + kTcHeadFloats) * 4 : 0;   // [class * Dc/32 + chunk | then 3 heads per group][sum | sum of squares][32 channels]
     o = (o + 127) / 128 * 128;
     s.ring = o; o += (size_t)nstage * kTcStageBytes;
@@ -320,6 +297,7 @@ struct TcMaps {
 template <int CP, int CE, bool SUMS, bool WANT_DIST, bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedParams p, const __grid_constant__ TcMaps maps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const long long t_entry = PROF ? clock64() : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = CE > 0 ? CE : p.C;      // CE: class count known at compile time (19 in every OnDA config) -> no k < C predication
     const int D = p.D, HW = p.HW;
@@ -328,8 +306,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     const int nstage = p.nstage;
     const int c_base = 0;                 // first channel of this CTA's slice
     const TcSmem L = tc_smem(Dc, C, CP, SUMS, nstage);
-    float* Bhi = reinterpret_cast<float*>(smem_raw + L.bhi);
-    float* Blo = reinterpret_cast<float*>(smem_raw + L.blo);
+    float* Btab = reinterpret_cast<float*>(smem_raw + L.btab);
     float* acc = reinterpret_cast<float*>(smem_raw + L.acc);
     float* out_stage = reinterpret_cast<float*>(smem_raw + L.out);
     float* mus = reinterpret_cast<float*>(smem_raw + L.mu);
@@ -381,12 +358,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         }
         mbar_init(btab_bar, 1);
         fence_barrier_init();
-        // B operand tables (hi, lo) of this CTA's channel slice: two bulk asynchronous copies, off everybody's
-        // critical path -- only the MMA issuer waits for them, before its first MMA
-        const uint32_t bytes = (uint32_t)(T.BR * Dc) * 4u;
-        mbar_arrive_tx(btab_bar, 2u * bytes);
-        bulk_g2s_plain(smem_u32(Bhi), p.table + T.off_qhi + (size_t)c_base * T.BR, bytes, btab_bar);
-        bulk_g2s_plain(smem_u32(Blo), p.table + T.off_qlo + (size_t)c_base * T.BR, bytes, btab_bar);
+        // B operand table of this CTA's channel slice: one bulk asynchronous copy, off everybody's critical path -- only
+        // the MMA issuer waits for it, before its first MMA
+        const uint32_t bytes = (uint32_t)(2 * T.BR * Dc) * 4u;
+        mbar_arrive_tx(btab_bar, bytes);
+        bulk_g2s_plain(smem_u32(Btab), p.table + T.off_b + (size_t)c_base * 2 * T.BR, bytes, btab_bar);
     }
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
@@ -417,6 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         // =========================== converters ========================================
         reg_inc<kTcRegsConv>();
         const int quarter = warp & 3, group = warp >> 2;
+        const int cbar = 7 + group;          // named barrier of the group (128 threads)
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
         const uint32_t lane_word = 4u * (uint32_t)(32 * quarter + lane);
         int stage = group;                   // ring stage of chunk q = q % nstage, phase (q / nstage) & 1
@@ -428,7 +405,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const int par = t & 1;
             const int as = q & (kTcAStages - 1);
             const uint32_t use = (uint32_t)q >> 2;
-            mbar_wait_t<64>(ring_full(stage), rphase, prof, dbg[0]);
+            if (quarter == 0) mbar_wait_t(ring_full(stage), rphase, prof, dbg[0]);      // one warp of the group watches the
+            named_bar_sync(cbar, 128);                                                       // mbarrier, the others sleep in the barrier
             {   // the 32 channel rows of this lane's pixel: row j sits in slot 8*(j%4) + j/4 and starts shift[j%4] floats in
                 const uint32_t sbase = ring + (uint32_t)stage * kTcStageBytes + lane_word;
 #pragma unroll
@@ -438,8 +416,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             if (lane == 0) mbar_arrive(ring_empty(stage));      // this warp's reads of the stage are issued and ordered before the arrive
             stage += kTcConvGroups;
             if (stage >= nstage) { stage -= nstage; rphase ^= 1; }
-            if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[1]);   // partial columns [par] of tile t-2 consumed
-            mbar_wait_t<64>(empty_a(as), (use & 1) ^ 1, prof, dbg[2]);
+            if (quarter == 0) {
+                if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[1]);   // partial columns [par] of tile t-2 consumed
+                mbar_wait_t(empty_a(as), (use & 1) ^ 1, prof, dbg[2]);
+            }
+            named_bar_sync(cbar, 128);
             tc_fence_after();
             const long long t_cv0 = prof ? clock64() : 0;
             uint64_t a2 = 0;                       // sum_j w_j x'_j^2 of the even / odd channels (packed f32x2 math)
@@ -510,8 +491,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 while (stage >= nstage) { stage -= nstage; rphase ^= 1; }
             }
             const int par = t & 1;
-            mbar_wait_t<64>(sort_ready(par), ((uint32_t)t >> 1) & 1, prof, dbg[1]);
-            mbar_wait_t<64>(ring_full(stage), rphase, prof, dbg[0]);
+            if (quarter == 0) {              // one warp of the group watches the mbarriers, the others sleep in the barrier
+                mbar_wait_t(sort_ready(par), ((uint32_t)t >> 1) & 1, prof, dbg[1]);
+                mbar_wait_t(ring_full(stage), rphase, prof, dbg[0]);
+            }
+            named_bar_sync(gbar, 128);
             const long long t_seg0 = prof ? clock64() : 0;
             const uint32_t row_lane = ring + (uint32_t)stage * kTcStageBytes + lane_off;
             const uint32_t eo = smem_u32(eoff + par * kTilePixels + 32 * quarter);     // byte offsets of this range's 32 pixels in a row
@@ -637,14 +621,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                     for (int k = 0; k < CP; ++k) pri[k] = 0.f;
                 }
             }
-            mbar_wait_t<400>(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
+            if (warp == kTcEpiWarp0) mbar_wait_t(acc_full(par), ((uint32_t)t >> 1) & 1, prof, dbg[0]);
+            named_bar_sync(2, 128);
             tc_fence_after();
-            // the three accumulators of the split (hi.hi | hi.lo | lo.hi): small terms first
+            // the three terms of the split: hi.hi in columns [0, BR), hi.lo in [BR, 2 BR), lo.hi in [64, 64 + BR): small terms first
             const uint32_t dcol = tmem_base + lane_base + kAccCol0 + (uint32_t)par * kAccSet;
             float d2[CP];
             {
                 uint32_t u[CP], v[CP];
-                tc_ld_cols<CP>(dcol + 32, u);
+                tc_ld_cols<CP>(dcol + (uint32_t)T.BR, u);
                 tc_ld_cols<CP>(dcol + 64, v);
                 tc_wait_ld();
 #pragma unroll
@@ -688,39 +673,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         // The whole warp walks the loop (uniform control flow); one elected lane issues.  Descriptors are the chunk's
         // base descriptor plus a constant per K-step (the address field counts 16-byte units; 8 channels = 64 units).
         {
-            const uint32_t idesc = make_idesc_tf32(128, 32);
-            const uint32_t lbo = 16u * (uint32_t)T.BR;       // bytes between 4-channel slabs of the B tables
-            const uint64_t bhi0 = make_bdesc(smem_u32(Bhi), lbo, 128), blo0 = make_bdesc(smem_u32(Blo), lbo, 128);
-            const uint32_t kstep = 2u * (uint32_t)T.BR;      // one K-step = 8 channels = two slabs, in the descriptor's 16-byte units
-            mbar_wait<32>(btab_bar, 0);             // the B tables have landed (bulk copies of the prologue)
+            const uint32_t idesc64 = make_idesc_tf32(128, 64), idesc32 = make_idesc_tf32(128, 32);
+            const uint32_t lbo = 32u * (uint32_t)T.BR;       // bytes between 4-channel slabs of the B table
+            const uint64_t b0 = make_bdesc(smem_u32(Btab), lbo, 128);
+            const uint32_t kstep = 4u * (uint32_t)T.BR;      // one K-step = 8 channels = two slabs, in the descriptor's 16-byte units
+            mbar_wait(btab_bar, 0);             // the B table has landed (bulk copy of the prologue)
             int q = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 const int par = t & 1;
                 if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
-                const uint32_t d0 = tmem_base + kAccCol0 + (uint32_t)par * kAccSet, d1 = d0 + 32, d2 = d0 + 64;
+                const uint32_t d0 = tmem_base + kAccCol0 + (uint32_t)par * kAccSet, d1 = d0 + 64;
                 for (int b = 0; b < NB; ++b, ++q) {
                     const int as = q & (kTcAStages - 1);
                     const uint32_t use = (uint32_t)q >> 2;
-                    mbar_wait_t<32>(full_a(as), use & 1, prof, dbg[1]);
+                    mbar_wait_t(full_a(as), use & 1, prof, dbg[1]);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_hi = tmem_base + (uint32_t)as * 64, a_lo = a_hi + 32;
-                        const uint64_t d_hi = bhi0 + (uint64_t)((uint32_t)b * 4u * kstep), d_lo = blo0 + (uint64_t)((uint32_t)b * 4u * kstep);
-                        // term i of the split accumulates in its own columns; the first MMAs of a tile overwrite them
+                        const uint64_t bd = b0 + (uint64_t)((uint32_t)b * 4u * kstep);
+                        // hi(x') against the hi and lo rows at once (64 classes wide: columns [0, BR) and [BR, 2 BR) of d0),
+                        // lo(x') against the hi rows (d1); the first MMAs of a tile overwrite the accumulators
                         if (b == 0) {
-                            tc_mma_tf32<0>(d0, a_hi, d_hi, idesc);
-                            tc_mma_tf32<0>(d1, a_hi, d_lo, idesc);
-                            tc_mma_tf32<0>(d2, a_lo, d_hi, idesc);
+                            tc_mma_tf32<0>(d0, a_hi, bd, idesc64);
+                            tc_mma_tf32<0>(d1, a_lo, bd, idesc32);
                         } else {
-                            tc_mma_tf32<1>(d0, a_hi, d_hi, idesc);
-                            tc_mma_tf32<1>(d1, a_hi, d_lo, idesc);
-                            tc_mma_tf32<1>(d2, a_lo, d_hi, idesc);
+                            tc_mma_tf32<1>(d0, a_hi, bd, idesc64);
+                            tc_mma_tf32<1>(d1, a_lo, bd, idesc32);
                         }
 #pragma unroll
                         for (int ks = 1; ks < 4; ++ks) {
-                            tc_mma_tf32<1>(d0, a_hi + ks * 8, d_hi + (uint64_t)(ks * kstep), idesc);
-                            tc_mma_tf32<1>(d1, a_hi + ks * 8, d_lo + (uint64_t)(ks * kstep), idesc);
-                            tc_mma_tf32<1>(d2, a_lo + ks * 8, d_hi + (uint64_t)(ks * kstep), idesc);
+                            tc_mma_tf32<1>(d0, a_hi + ks * 8, bd + (uint64_t)(ks * kstep), idesc64);
+                            tc_mma_tf32<1>(d1, a_lo + ks * 8, bd + (uint64_t)(ks * kstep), idesc32);
                         }
                         tc_commit(empty_a(as));             // A stage reusable once these MMAs retire
                         if (b == NB - 1) tc_commit(acc_full(par));      // accumulator complete
@@ -746,7 +729,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 int npx;
                 tile_of(t, img, pix0, npx);
                 for (int b = 0; b < NB; ++b) {
-                    mbar_wait_t<64>(ring_empty(stage), rphase ^ 1, prof, dbg[0]);
+                    mbar_wait_t(ring_empty(stage), rphase ^ 1, prof, dbg[0]);
                     const uint32_t dst = ring + (uint32_t)stage * kTcStageBytes;
                     const uint32_t bar = ring_full(stage);
                     mbar_arrive_tx(bar, (uint32_t)kTcStageBytes);
@@ -820,7 +803,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 const int val = __shfl_sync(0xffffffffu, lane | ((cstart >> 5) << 8), who ? __ffs(who) - 1 : 0);
                 cutcls[c] = who ? val : -1;
             }
-            if (t >= 2) mbar_wait_t<400>(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);   // summers are done with tile t-2
+            if (t >= 2) {                                                                    // summers are done with tile t-2
+                if (sw == 0) mbar_wait_t(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
+                named_bar_sync(1, 64);
+            }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int v = 2 * sw + r;
@@ -849,13 +835,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     }   // last warpgroup
 
     // ---- teardown: publish the class partials, release tensor memory
-    if (PROF && p.debug != nullptr && lane == 0) {
-        long long* d = p.debug + ((size_t)blockIdx.x * 32 + warp) * 8;
-        dbg[7] = clock64() - t_start;
-        for (int i = 0; i < 8; ++i) d[i] = dbg[i];
-    }
+    const long long t_role_end = PROF ? clock64() : 0;
     tc_fence_before();
     __syncthreads();
+    const long long t_sync_end = PROF ? clock64() : 0;
     if (SUMS) {
         float* out = p.cta_partials + (size_t)blockIdx.x * sums_floats(C, D);
         const int cd = C * Dc;
@@ -868,6 +851,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     if (warp == kTcMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+    if (PROF && p.debug != nullptr && lane == 0) {
+        long long* d = p.debug + ((size_t)blockIdx.x * 32 + warp) * 8;
+        dbg[7] = t_role_end - t_start;
+        dbg[4] = t_start - t_entry;                 // prologue
+        dbg[5] = t_sync_end - t_role_end;           // waiting for the slowest role
+        dbg[6] = clock64() - t_sync_end;            // writing the partials / releasing tensor memory
+        for (int i = 0; i < 8; ++i) d[i] = dbg[i];
     }
 }
 
@@ -941,15 +932,6 @@ static int launch_tc(FusedParams p, int grid, cudaStream_t stream) {
     if (smem > smem_set[dev]) {
         ONDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set[dev] = smem;
-    }
-    {   // experiment switch (ONDA_TC_WAIT)
-        static int mode_set = -1;
-        const char* e = getenv("ONDA_TC_WAIT");
-        const int mode = e ? atoi(e) : 1;
-        if (mode != mode_set) {
-            ONDA_CUDA_TRY(cudaMemcpyToSymbol(g_tc_wait_mode, &mode, sizeof(int)));
-            mode_set = mode;
-        }
     }
     TcMaps maps;
     const int rc = tc_make_maps(p.feat, p.B, p.D, p.HW, &maps);

@@ -25,10 +25,20 @@ names = {"converter": (0, 8, ["wait ring_full", "wait acc_empty", "wait empty_a(
          "summer": (8, 24, ["wait ring_full", "wait sort_ready", "-", "class-sum loop"]),
          "epilogue": (24, 28, ["wait acc_full"]), "sorter": (28, 30, ["wait sort_free"]),
          "mma": (30, 31, ["wait acc_empty", "wait full_a"]), "producer": (31, 32, ["wait ring_empty"])}
-print("mean total cycles per warp:", tot[:, :32].mean().item())
+print("mean total cycles per warp:", tot[:, :32].mean().item(), " max over CTAs:", tot[:, :32].mean(dim=1).max().item())
+print("prologue cycles (mean):", d[:, :, 4].mean().item(), " wait-for-slowest-role:", d[:, :, 5].mean().item(), " teardown:", d[:, :, 6].mean().item())
 for role, (a, b, labels) in names.items():
     t = tot[:, a:b].mean().item()
     print(f"{role:9s} total {t:10.0f} cyc")
     for i, lab in enumerate(labels):
         v = d[:, a:b, i].mean().item()
         print(f"     {lab:24s} {v:10.0f} cyc  {100 * v / t:5.1f}%")
+# per-CTA spread: CTAs 0..(tiles % grid - 1) carry one tile more than the rest
+per_cta = tot[:, 24:28].mean(dim=1)          # epilogue warps: the last role to finish
+import math
+tiles = 32 * math.ceil(65 * 129 / 128)
+extra = tiles % 148
+a, b = per_cta[:extra], per_cta[extra:]
+print(f"CTAs with {tiles // 148 + 1} tiles: n={len(a)} mean {a.mean().item():.0f} min {a.min().item():.0f} max {a.max().item():.0f}")
+print(f"CTAs with {tiles // 148} tiles: n={len(b)} mean {b.mean().item():.0f} min {b.min().item():.0f} max {b.max().item():.0f}")
+print("per-CTA cycles / tile, sorted deciles:", [round(x) for x in torch.quantile(torch.cat([a / (tiles // 148 + 1), b / (tiles // 148)]), torch.linspace(0, 1, 11).double()).tolist()])
