@@ -142,14 +142,16 @@ int onda_append_update(float* prototypes, float* squared_mean, float* counter, c
 
 /* ---- switch statistics / prior mix ------------------------------------------ */
 /*
- * prior[b,k,p] = sum_i coef[i] * softmax_k(logits_i[b,:,p]) over the non-NULL inputs (i < 3), written to
+ * prior[b,k,p] = (coef0 * softmax_k(logits_0) + coef1 * softmax_k(logits_1)) * scale01 + coef2 * softmax_k(logits_2)
+ * over the non-NULL inputs, every product and sum rounded to fp32 in this order (scale01 is the h-switch's
+ * `prior *= percentage_static`, prototypes_hswitch.py:56; pass 1 otherwise), written to
  * `prior_out` (may be NULL: statistics only), and stats_out[0..2] = sum_n max_k softmax(logits_i)[n,k],
  * stats_out[3] = sum_n max_k prior[n,k], stats_out[4] = N.  Replaces the softmax / max / mean chains of
  * prototypes_hybrid_switch.py:52-88, prototypes_hswitch.py:30-68, prototypes_vswitch.py:40-70 and
  * prototypes.py:213-250.  stats_out holds 8 floats and is overwritten.
  */
 int onda_prior_mix_stats(const float* logits0, const float* logits1, const float* logits2,
-                         float coef0, float coef1, float coef2, int B, int C, int HW,
+                         float coef0, float coef1, float coef2, float scale01, int B, int C, int HW,
                          float* prior_out, float* stats_out, void* workspace, size_t workspace_bytes,
                          void* stream);
 

@@ -42,7 +42,7 @@ _SIGNATURES = {
     "onda_ema_update": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_float, _p]),
     "onda_ema_update_and_table": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_float, C.c_int, _p, _p]),
     "onda_append_update": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, _p]),
-    "onda_prior_mix_stats": (C.c_int, [_p, _p, _p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+    "onda_prior_mix_stats": (C.c_int, [_p, _p, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                        _p, _p, _p, C.c_size_t, _p]),
     "onda_prior_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "onda_step_log_workspace_bytes": (C.c_size_t, []),

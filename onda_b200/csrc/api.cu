@@ -340,7 +340,7 @@ constexpr int kPriorThreads = 256;
 template <int CP>
 __global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* __restrict__ l0, const float* __restrict__ l1,
                                                                   const float* __restrict__ l2, float c0, float c1, float c2,
-                                                                  int B, int C, int HW, float* __restrict__ prior_out,
+                                                                  float scale01, int B, int C, int HW, float* __restrict__ prior_out,
                                                                   float* __restrict__ partials, unsigned* __restrict__ ticket,
                                                                   float* __restrict__ stats_out) {
     __shared__ float red[kPriorThreads / 32][kStatSlots];
@@ -359,7 +359,13 @@ __global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* _
         for (int k = 0; k < CP; ++k) mix[k] = 0.f;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            if (src[i] == nullptr) continue;
+            if (src[i] == nullptr) {
+                if (i == 1) {
+#pragma unroll
+                    for (int k = 0; k < CP; ++k) mix[k] = __fmul_rn(mix[k], scale01);
+                }
+                continue;
+            }
             float z[CP];
             float zmax = -__int_as_float(0x7f800000);
 #pragma unroll
@@ -387,6 +393,10 @@ __global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* _
                 }
             }
             st[i] += pmax;                                    // .max(axis=1)[0].mean(), :54, :62, :81
+            if (i == 1) {                                     // h-switch: prior *= percentage_static (prototypes_hswitch.py:56)
+#pragma unroll
+                for (int k = 0; k < CP; ++k) mix[k] = __fmul_rn(mix[k], scale01);
+            }
         }
         float mmax = -__int_as_float(0x7f800000);
 #pragma unroll
@@ -880,8 +890,8 @@ size_t onda_prior_workspace_bytes(int B, int C, int HW) {
 }
 
 int onda_prior_mix_stats(const float* logits0, const float* logits1, const float* logits2, float coef0, float coef1,
-                         float coef2, int B, int C, int HW, float* prior_out, float* stats_out, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+                         float coef2, float scale01, int B, int C, int HW, float* prior_out, float* stats_out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
     ONDA_REQUIRE(stats_out && workspace, "onda_prior_mix_stats: null stats/workspace");
     ONDA_REQUIRE(logits0 || logits1 || logits2, "onda_prior_mix_stats: no input");
     ONDA_REQUIRE(B > 0 && HW > 0 && C > 0 && C <= ONDA_MAX_CLASSES, "onda_prior_mix_stats: bad shape");
@@ -893,10 +903,10 @@ int onda_prior_mix_stats(const float* logits0, const float* logits1, const float
     unsigned* ticket = (unsigned*)workspace;  // zero on first use; the kernel re-arms it
     float* partials = (float*)((char*)workspace + 256);
     if (padded_classes(C) == 20)
-        prior_mix_kernel<20><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>(logits0, logits1, logits2, coef0, coef1, coef2, B,
+        prior_mix_kernel<20><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>(logits0, logits1, logits2, coef0, coef1, coef2, scale01, B,
                                                                                C, HW, prior_out, partials, ticket, stats_out);
     else
-        prior_mix_kernel<32><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>(logits0, logits1, logits2, coef0, coef1, coef2, B,
+        prior_mix_kernel<32><<<grid, kPriorThreads, 0, (cudaStream_t)stream>>>(logits0, logits1, logits2, coef0, coef1, coef2, scale01, B,
                                                                                C, HW, prior_out, partials, ticket, stats_out);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);

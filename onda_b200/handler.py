@@ -357,11 +357,13 @@ class prototype_handler:
         return labels
 
     # ------------------------------------------------------------------ prior mix / switch statistics
-    def prior_mix(self, logits, coefs, write_prior=True):
+    def prior_mix(self, logits, coefs, write_prior=True, scale01=1.0):
         """Softmax-mix of up to three logit maps and their batch confidences, in one pass.
 
         ``logits``: sequence of up to 3 tensors (B, C, h, w) or None; ``coefs``: their weights.
-        Returns ``(prior, conf, prior_conf)`` where ``prior = sum_i coefs[i]*softmax(logits[i], 1)``
+        Returns ``(prior, conf, prior_conf)`` where ``prior = (coefs[0]*softmax(logits[0], 1) + coefs[1]*softmax(logits[1],
+        1)) * scale01 + coefs[2]*softmax(logits[2], 1)`` (every step rounded like the reference's tensor expression;
+        ``scale01`` is the h-switch's ``percentage_static``)
         as a (B, C, h, w) tensor (None if ``write_prior`` is False), ``conf[i] = mean_n max_k
         softmax(logits[i])`` (None for missing inputs) and ``prior_conf = mean_n max_k prior``.
         Replaces the softmax/max/mean chains of prototypes_hybrid_switch.py:52-88 (and the
@@ -386,7 +388,7 @@ class prototype_handler:
         work = self._buf("prior_work", (wbytes,), torch.uint8, device, zero=True)
         nat.check(self._lib.onda_prior_mix_stats(
             nat.ptr(dense[0]), nat.ptr(dense[1]), nat.ptr(dense[2]), float(coefs[0]), float(coefs[1]), float(coefs[2]),
-            B, C, HW, nat.ptr(prior), nat.ptr(stats), nat.ptr(work), wbytes, _stream_ptr(device)), "onda_prior_mix_stats")
+            float(scale01), B, C, HW, nat.ptr(prior), nat.ptr(stats), nat.ptr(work), wbytes, _stream_ptr(device)), "onda_prior_mix_stats")
         if self.process_group is not None:
             import torch.distributed as dist
             dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.process_group)

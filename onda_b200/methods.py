@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import torch
 
-from .switching import static_share
+from .switching import below_f32, static_share
 
 
 def _missing(v):
@@ -128,9 +128,10 @@ def hswitch_prototype_predictions(method, batch):
             _, pred_dyn = method.dynamic_model(image)
             out_dyn = pred_dyn["out"]
             _record_ece(method, "dynamic", out_dyn, batch.get("label", 0))
+        # prior = (l_e p_e + l_s p_s) * share + ((1 - share) * l_d) * p_d, rounded in the reference's order (:36-68)
         prior, conf, prior_conf = handler.prior_mix(
             [pred_ema["out"], out_static, out_dyn],
-            [share * spec.EMA_LAMBDA, share * lam_s, (1 - share) * spec.DYNAMIC_LAMBDA if out_dyn is not None else 0.0])
+            [spec.EMA_LAMBDA, lam_s, (1 - share) * spec.DYNAMIC_LAMBDA if out_dyn is not None else 0.0], scale01=share)
         if out_dyn is not None:
             monitor.add({"prior dynamic": conf[2]})
     return _finish(method, batch, pred_ema, prior, prior_conf)
@@ -150,7 +151,7 @@ def base_prototype_predictions(method, batch):
             _record_ece(method, "static", out_static, batch.get("label", 0))
         thresh = 0 if _missing(spec.SWITCH_PRIOR_THRESH) else spec.SWITCH_PRIOR_THRESH
         calculate_dyn, replace_dyn = True, False
-        if thresh > 0 and monitor.avg("prior static") < thresh:
+        if thresh > 0 and below_f32(monitor.avg("prior static"), thresh):
             replace_dyn = True
         elif thresh > 0:
             calculate_dyn = False

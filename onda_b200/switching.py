@@ -14,7 +14,6 @@ full -- SURVEY.md appendix B).
 """
 from __future__ import annotations
 
-from collections import deque
 from statistics import median
 
 import numpy as np
@@ -154,7 +153,17 @@ class DevSelect:
 
 
 def static_share(median_static, soft_trans, switch_prior_thresh=0.0):
-    """Fraction of the prior taken from the static model by the h-switch."""
+    """Fraction of the prior taken from the static model by the h-switch (prototypes_hswitch.py:45-55).
+
+    The reference's Monitor holds 0-dim float32 tensors there, so its ramp ``vl * (25/3) - 41/6`` and its comparison
+    with the threshold are float32 operations; reproduced with numpy float32 scalars."""
+    v = np.float32(median_static)
     if soft_trans:
-        return max(min(median_static * (25.0 / 3) - (41.0 / 6), 1), 0)
-    return int(median_static > switch_prior_thresh)
+        ramp = np.float32(v * np.float32(25.0 / 3)) - np.float32(41.0 / 6)
+        return float(max(min(ramp, np.float32(1)), np.float32(0)))
+    return int(v > np.float32(switch_prior_thresh))
+
+
+def below_f32(value, threshold):
+    """``value < threshold`` the way the reference evaluates it on a 0-dim float32 tensor (prototypes.py:231-233)."""
+    return bool(np.float32(value) < np.float32(threshold))

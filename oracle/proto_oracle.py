@@ -408,9 +408,11 @@ class OracleDevSelect:
 
 def hswitch_percentage(median_static: float, soft_trans: bool, switch_thresh: float = 0.0):
     """Reference: prototypes_hswitch.py:45-55."""
+    # the reference evaluates this on a 0-dim float32 tensor (Monitor.avg of tensors): float32 arithmetic
+    v = torch.tensor(float(median_static), dtype=torch.float32)
     if soft_trans:
-        return max(min(median_static * (25.0 / 3) - (41.0 / 6), 1), 0)
-    return int(median_static > switch_thresh)
+        return float(max(min(v * (25.0 / 3) - (41.0 / 6), 1), 0))
+    return int(v > switch_thresh)
 
 
 def hybrid_prior(logits_ema, logits_static, logits_dynamic, monitor: OracleMonitor,

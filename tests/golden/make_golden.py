@@ -33,6 +33,8 @@ from framework.utils.monitoring import Monitor  # noqa: E402
 from framework.utils.func import prob_2_entropy  # noqa: E402
 import framework.domain_adaptation.methods.prototypes_hybrid_switch as ref_hybrid  # noqa: E402
 import framework.domain_adaptation.methods.prototypes_vswitch as ref_vswitch  # noqa: E402
+import framework.domain_adaptation.methods.prototypes_hswitch as ref_hswitch  # noqa: E402
+import framework.domain_adaptation.methods.prototypes as ref_base  # noqa: E402
 
 from oracle.proto_oracle import synth_case  # noqa: E402  (seeded input generator only)
 
@@ -172,7 +174,8 @@ def monitor_trace():
             ema.append(mon.exp("prior static"))
             vcur.append(vsel.current)
             vl = mon.avg("prior static")
-            pct.append(max(min(vl * (25.0 / 3) - (41.0 / 6), 1), 0))  # prototypes_hswitch.py:47
+            vt = torch.tensor(vl, dtype=torch.float32)    # hswitch_proDA keeps 0-dim float32 tensors in its Monitor
+            pct.append(float(max(min(vt * (25.0 / 3) - (41.0 / 6), 1), 0)))  # prototypes_hswitch.py:47
         npz(f"monitor_trace_{tag}.npz", conf=conf, limit=np.int64(args[0]), exp_const=np.float64(args[1]),
             dev_func=np.array(args[2]), gray=np.array([0.83, 0.9]), dev_thresh=np.float64(0.0002),
             vthresh=np.float64(0.00028),
@@ -308,6 +311,87 @@ def method_case():
         **{f"ref_stat_{k.replace(' ', '_')}": np.array(v) for k, v in stat.items()}, **state)
 
 
+def method_variant_case(name, yml, key, cls, steps=44, wave=(0.07, 0.3), overrides=None):
+    """The other three method classes (a11): the REAL hswitch_proDA / vswitch_proDA / online_proDA
+    ``prototype_predictions`` followed by ``ma`` over a stream whose logit sharpness (hence the static confidence)
+    rises and falls, so the switch takes both branches."""
+    import yaml
+    with open(os.path.join(REF, "configs", yml)) as f:
+        cfg = to_attr(yaml.safe_load(f))
+    cfg.OTHERS.DEVICE = "cpu"
+    cfg.NUM_CLASSES = 19
+    cfg.OTHERS.SNAPSHOT_DIR = "/tmp/onda_golden_snap"
+    spec = cfg.METHOD.ADAPTATION[key]
+    spec.set_ = "golden"
+    spec.LOAD_PROTO = AttrDict()
+    spec.AVG_MONITOR_SIZE = 12
+    for k, v in (overrides or {}).items():
+        spec[k] = v
+    method = cls(FakeSegModel(), cfg, spec)
+    for m in (method.ema_model, method.dynamic_model, method.static_model, method.model):
+        m.eval()
+    with torch.no_grad():
+        method.dynamic_model.head.weight.mul_(1.5)
+    seed = 10 + len(name)
+    rs = np.random.RandomState(seed)      # legacy stream: stable across numpy versions, so only the seed is stored
+    first = synth_case(31, 1, 24, 5, 5)
+    method.prototypes.prototypes = first["protos"].clone() * 0.2
+    method.prototypes.squared_mean = (first["protos"] * 0.2) ** 2 + 1.0
+    method.prototypes.counter = first["counter"].clone()
+    keys = ["prior static", "prior", "prototypes", "pseudolabel confidence"]
+    images, labs, softs, sel, stat, share = [], [], [], [], {k: [] for k in keys}, []
+    for i in range(steps):
+        scale = wave[0] + wave[1] * (0.5 + 0.5 * np.sin(i / 5.0))
+        img = torch.from_numpy(rs.standard_normal((1, 3, 32, 56)).astype(np.float32) * np.float32(scale))
+        pred = method.prototype_predictions({"image": img, "label": 0})
+        method.prototypes.ma(pred["ema_model"]["feat"], pred["ema_model"]["out"])
+        images.append(img)
+        labs.append(pred["pseudolabels"])
+        softs.append(pred["soft_predictions"])
+        sel.append(method.model_select.current if hasattr(method, "model_select") else -1)
+        cur = method.intensity_ma.current_dict
+        share.append(float(cur["percentage_static"][-1]) if "percentage_static" in cur else -1.0)
+        for k in keys:
+            stat[k].append(float(cur[k][-1]))
+    state = {}
+    for nm, m in (("ema", method.ema_model), ("static", method.static_model), ("dynamic", method.dynamic_model)):
+        for k, v in m.state_dict().items():
+            state[f"w_{nm}_{k.replace('.', '_')}"] = v
+    n_dyn = len(method.intensity_ma.current_dict.get("prior dynamic", []))
+    print(name, "static conf range", min(stat["prior static"]), max(stat["prior static"]), "select", sel, "share", share,
+          "dynamic forwards recorded", n_dyn)
+    thr = spec.SWITCH_PRIOR_THRESH
+    npz(name, image_seed=np.int64(seed), image_scales=np.array([wave[0] + wave[1] * (0.5 + 0.5 * np.sin(i / 5.0)) for i in range(steps)]),
+        image_checksum=np.float64(torch.stack(images).double().sum().item()),
+        ref_labels=torch.stack(labs), ref_soft=torch.stack(softs),
+        ref_select=np.array(sel), ref_share=np.array(share), init_protos=first["protos"] * 0.2,
+        init_sq_mean=(first["protos"] * 0.2) ** 2 + 1.0, init_counter=first["counter"],
+        ref_final_protos=method.prototypes.prototypes, ref_final_sq_mean=method.prototypes.squared_mean,
+        limit=np.int64(spec.AVG_MONITOR_SIZE), exp_const=np.float64(spec.EXP_MONITOR_CONST),
+        ma_lambda=np.float64(spec.MA_LAMBDA), tau=np.float64(spec.TAU), thresh=np.float64(spec.PSEUDO_THRESH),
+        ema_lambda=np.float64(spec.EMA_LAMBDA), static_lambda=np.float64(spec.STATIC_LAMBDA),
+        dynamic_lambda=np.float64(spec.DYNAMIC_LAMBDA), soft_trans=np.int64(1 if spec.SOFT_TRANS is True else 0),
+        switch_prior_thresh=np.float64(thr if not isinstance(thr, dict) else 0.0),
+        **{f"ref_stat_{k.replace(' ', '_')}": np.array(v) for k, v in stat.items()}, **state)
+
+
+def method_variants():
+    H, V, B = ref_hswitch.hswitch_proDA, ref_vswitch.vswitch_proDA, ref_base.online_proDA
+    # h-switch, soft transition: the ramp 25/3 * median - 41/6 sweeps (0.82, 0.94)
+    method_variant_case("method_hswitch_soft.npz", "confidence_switch.yml", "PROTO_ONLINE_HSWITCH", H, wave=(0.25, 0.9))
+    # h-switch, hard transition at SWITCH_PRIOR_THRESH, with an EMA share in the mix
+    method_variant_case("method_hswitch_hard.npz", "confidence_switch.yml", "PROTO_ONLINE_HSWITCH", H, wave=(0.25, 0.9),
+                        overrides={"SOFT_TRANS": False, "SWITCH_PRIOR_THRESH": 0.88, "EMA_LAMBDA": 0.25})
+    # v-switch: derivative of the static confidence against SWITCH_PRIOR_THRESH (its threshold_c)
+    method_variant_case("method_vswitch.npz", "confidence_der_switch.yml", "PROTO_ONLINE_VSWITCH", V,
+                        overrides={"SWITCH_PRIOR_THRESH": 0.002})
+    # base class: additive three-way mix (threshold 0) and the replace / skip rule (threshold > 0)
+    method_variant_case("method_base_mix.npz", "dynamic_model.yml", "PROTO_ONLINE", B,
+                        overrides={"STATIC_LAMBDA": 0.5, "EMA_LAMBDA": 0.25, "DYNAMIC_LAMBDA": 0.25})
+    method_variant_case("method_base_rule.npz", "dynamic_model.yml", "PROTO_ONLINE", B, wave=(0.25, 0.9),
+                        overrides={"STATIC_LAMBDA": 1, "SWITCH_PRIOR_THRESH": 0.88})
+
+
 def stats_case():
     """Switch statistics and the entropy map on raw logits (K4 parity)."""
     case = synth_case(61, 2, 8, 11, 17)
@@ -400,6 +484,7 @@ def main():
     sequence_case()
     stats_case()
     method_case()
+    method_variants()
 
 
 if __name__ == "__main__":

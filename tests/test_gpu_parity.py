@@ -25,7 +25,8 @@ IMPLS = ["simt", "tcgen05"]
 
 
 def need_shape(impl, D, C=19):
-    """The tcgen05 kernel covers D % 32 == 0, 128 <= D <= 256, C <= 32; everything else is the CUDA-core kernel."""
+    """The tcgen05 kernel covers what onda_impl_supported reports (D % 64 == 0, C <= 32); everything else is the
+    CUDA-core kernel."""
     from onda_b200 import _native as nat
     if impl == "tcgen05" and not nat.load().onda_impl_supported(1, D, 128, C, nat.IMPL["tcgen05"]):
         pytest.skip(f"tcgen05 kernel does not cover D={D}, C={C}")
@@ -191,9 +192,11 @@ SHAPES = [
     (38, 5, 24, 1, 1, 19, "euclidean"),           # 5 pixels in total
     (39, 2, 320, 3, 51, 19, "mahalanobis"),       # HW = 153
     (40, 2, 128, 21, 13, 19, "mahalanobis"),      # tcgen05 range: D = 128, ragged last tile
-    (42, 3, 192, 5, 31, 7, "euclidean"),          # D = 192 (6 chunks), few classes
+    (42, 3, 192, 5, 31, 7, "euclidean"),          # D = 192 (6 chunks), few classes, H*W = 3 mod 4
     (43, 1, 128, 9, 14, 25, "mahalanobis"),       # 25 classes (32-wide epilogue), 126 pixels: a single partial tile
-    (44, 7, 160, 37, 53, 19, "mahalanobis"),      # D = 160 (5 chunks), 13727 pixels
+    (44, 7, 160, 37, 53, 19, "mahalanobis"),      # D = 160: not a multiple of 64 (CUDA-core kernel), 13727 pixels
+    (45, 2, 64, 16, 24, 19, "mahalanobis"),       # D = 64 (2 chunks), even H*W (all rows share one shift)
+    (46, 3, 256, 10, 13, 19, "mahalanobis"),      # H*W = 130 = 2 mod 4, a 2-pixel last tile
 ]
 
 
@@ -329,6 +332,66 @@ def test_hybrid_method_golden():
     close_rel_max(m.prototypes.squared_mean, z["ref_final_sq_mean"])
 
 
+def _variant_images(z):
+    rs = np.random.RandomState(int(z["image_seed"]))
+    imgs = [torch.from_numpy(rs.standard_normal((1, 3, 32, 56)).astype(np.float32) * np.float32(sc)) for sc in z["image_scales"]]
+    assert float(torch.stack(imgs).double().sum()) == pytest.approx(float(z["image_checksum"]), abs=1e-6)
+    return imgs
+
+
+VARIANTS = [
+    # fixture, methods.<function>, selector
+    ("method_hswitch_soft.npz", "hswitch_prototype_predictions", None),
+    ("method_hswitch_hard.npz", "hswitch_prototype_predictions", None),
+    ("method_vswitch.npz", "vswitch_prototype_predictions", "dev"),
+    ("method_base_mix.npz", "base_prototype_predictions", None),
+    ("method_base_rule.npz", "base_prototype_predictions", None),
+]
+
+
+@pytest.mark.parametrize("fixture,fn,selector", VARIANTS, ids=[v[0][7:-4] for v in VARIANTS])
+def test_method_variants_golden(fixture, fn, selector):
+    """hswitch_proDA / vswitch_proDA / online_proDA ``prototype_predictions`` + ``ma`` over 44 steps against runs of the
+    real reference classes (prototypes_hswitch.py:26-85, prototypes_vswitch.py:36-87, prototypes.py:208-273): same
+    static share / selector trace, labels, soft predictions, Monitor entries and final prototypes."""
+    from onda_b200 import Monitor, DevSelect, methods
+    z = np.load(os.path.join(GOLDEN, fixture))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    class Method:
+        pass
+    m = Method()
+    m.device = dev()
+    m.cfg_spec = _Spec(EMA_LAMBDA=float(z["ema_lambda"]), STATIC_LAMBDA=float(z["static_lambda"]),
+                       DYNAMIC_LAMBDA=float(z["dynamic_lambda"]), SOFT_TRANS=bool(int(z["soft_trans"])),
+                       SWITCH_PRIOR_THRESH=float(z["switch_prior_thresh"]))
+    m.intensity_ma = Monitor(int(z["limit"]), float(z["exp_const"]), "hamming")
+    if selector == "dev":
+        m.model_select = DevSelect(DevSelect.static, float(z["switch_prior_thresh"]))
+    m.ema_model, m.static_model, m.dynamic_model = (_FakeSegModel(z, n).to(dev()).eval() for n in ("ema", "static", "dynamic"))
+    m.prototypes = make_handler(T(z["init_protos"]), T(z["init_sq_mean"]), T(z["init_counter"]), "mahalanobis",
+                                tau=float(z["tau"]), thresh=float(z["thresh"]), ma_lambda=float(z["ma_lambda"]))
+    predict = getattr(methods, fn)
+    select, share = [], []
+    for i, img in enumerate(_variant_images(z)):
+        pred = predict(m, {"image": img, "label": 0})
+        m.prototypes.ma(pred["ema_model"]["feat"], pred["ema_model"]["out"])
+        cur = m.intensity_ma.current_dict
+        select.append(m.model_select.current if selector else -1)
+        share.append(float(cur["percentage_static"][-1]) if "percentage_static" in cur else -1.0)
+        ref_soft = T(z["ref_soft"][i])
+        assert float((pred["soft_predictions"].cpu() - ref_soft).abs().max()) <= 2e-5  # conv backbone on GPU adds ~1e-6
+        check_labels_loose(pred["pseudolabels"], T(z["ref_labels"][i]), ref_soft, np.float32(z["thresh"]))
+        for key in ("prior static", "prior", "prototypes", "pseudolabel confidence"):
+            assert cur[key][-1] == pytest.approx(float(z["ref_stat_" + key.replace(" ", "_")][i]), abs=3e-6), (i, key)
+    assert select == list(z["ref_select"])
+    # the h-switch ramp amplifies the confidence noise of the GPU convolution by 25/3
+    assert np.allclose(share, z["ref_share"], atol=5e-5)
+    close_rel_max(m.prototypes.prototypes, z["ref_final_protos"])
+    close_rel_max(m.prototypes.squared_mean, z["ref_final_sq_mean"])
+
+
 def check_labels_loose(labels, ref_labels, ref_soft, thresh, margin=1e-4):
     """Label check for inputs that went through a cuDNN convolution (feature noise ~1e-6)."""
     labels, ref_labels = labels.cpu().flatten(), ref_labels.flatten()
@@ -340,7 +403,42 @@ def check_labels_loose(labels, ref_labels, ref_soft, thresh, margin=1e-4):
 
 
 # --------------------------------------------------------------------------------------
-# full BASELINE sizes: size-independent properties (the oracle would take minutes here)
+# full BASELINE sizes against the oracle (1.4 s of CPU per 270k pixels at D = 256, ~10 s at D = 2048)
+# --------------------------------------------------------------------------------------
+FULL = [
+    (61, 32, 256, 65, 129),      # the bench workload: BASELINE configs[2] on one GPU
+    (62, 8, 256, 129, 257),      # BASELINE configs[3]: full resolution
+    (63, 4, 2048, 65, 129),      # BASELINE configs[0] width, four images
+]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("seed,B,D,h,w", FULL)
+def test_full_size_oracle_parity(seed, B, D, h, w, impl):
+    """Labels, soft predictions, statistics (entropy included) and the post-ma state at the sizes the bench times."""
+    need_shape(impl, D)
+    case = po.synth_case(seed, B, D, h, w)
+    hd = make_handler(case["protos"], case["sq_mean"], case["counter"], "mahalanobis", impl=impl)
+    orc = make_oracle(case["protos"], case["sq_mean"], case["counter"], "mahalanobis")
+    feat, prior, out = (case[k].to(dev()) for k in ("feat", "prior", "out"))
+    ref_labels, ref_soft = po.fused_step(orc, case["feat"], case["prior"], case["out"])
+    labels, soft = hd.pseudo_labels_fused(feat, prior, out)
+    hd.ma(feat, out)
+    assert float((soft.cpu() - ref_soft).abs().max()) <= 1e-5
+    check_labels(labels, ref_labels, ref_soft, np.float32(0.3))
+    close_rel_max(hd.prototypes, orc.prototypes)
+    close_rel_max(hd.squared_mean, orc.squared_mean)
+    st = hd.last_stats
+    assert st["pixels"] == B * h * w
+    assert st["pseudolabel confidence"] == pytest.approx(ref_soft.max(dim=1)[0].mean().item(), abs=1e-6)
+    assert st["pseudolabel_pixel_num"] == pytest.approx(float((ref_labels != 255).sum()), abs=2)
+    # prob_2_entropy (framework/utils/func.py:71-74) of the rectified posterior, summed over classes, batch mean
+    ref_entropy = po.normalised_entropy(ref_soft).sum(dim=1).double().mean().item()
+    assert st["entropy"] == pytest.approx(ref_entropy, abs=2e-6)
+
+
+# --------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties
 # --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("B,D,h,w", [(32, 256, 65, 129), (8, 256, 129, 257), (8, 2048, 65, 129)])

@@ -163,3 +163,17 @@ def test_widened_rows_match_reference():
     assert np.array_equal(arg.numpy(), z["eval_argmax"]) and np.array_equal(hist, z["eval_hist"])
     iu = np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist) + np.finfo(float).eps)
     assert np.array_equal(iu, z["eval_iu"])
+
+
+@pytest.mark.parametrize("fixture", ["method_hswitch_soft.npz", "method_hswitch_hard.npz"])
+def test_hswitch_share_restatement_matches_reference_trace(fixture):
+    """The h-switch ramp / threshold of the product (switching.static_share) and of the oracle reproduce the share the real
+    hswitch_proDA recorded at every step, given the reference's own static confidences."""
+    from onda_b200.switching import Monitor, static_share
+    z = np.load(os.path.join(GOLDEN, fixture))
+    mon = Monitor(int(z["limit"]), float(z["exp_const"]), "hamming")
+    for i, conf in enumerate(z["ref_stat_prior_static"]):
+        mon.add({"prior static": float(conf)})
+        share = static_share(mon.avg("prior static"), bool(int(z["soft_trans"])), float(z["switch_prior_thresh"]))
+        assert share == float(z["ref_share"][i]), i
+        assert po.hswitch_percentage(mon.avg("prior static"), bool(int(z["soft_trans"])), float(z["switch_prior_thresh"])) == share
