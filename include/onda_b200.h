@@ -126,6 +126,17 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
                            int B, int D, int HW, int C, float tau, float thresh,
                            int64_t* labels, float* soft, float* dist, float* sums,
                            void* workspace, size_t workspace_bytes, int impl, void* stream);
+/*
+ * Same, for a `sums` buffer that peers read over NVLink (onda_ema_update_and_table_allreduce): `sums` is written only
+ * once every flag peer_done[r] (r < peer_world, this rank's own "done" words) has reached *peer_epoch - 1, i.e. once
+ * every rank has finished reading what the buffer held for the previous exchange.  This makes a replayed CUDA graph
+ * of the step safe with a single peer-visible buffer.  peer_done == NULL: no guard.
+ */
+int onda_pseudolabel_fused_guarded(const float* feat, const float* prior, const float* logits, const float* table,
+                                   int B, int D, int HW, int C, float tau, float thresh,
+                                   int64_t* labels, float* soft, float* dist, float* sums,
+                                   void* workspace, size_t workspace_bytes, int impl,
+                                   const uint32_t* peer_done, const uint32_t* peer_epoch, int peer_world, void* stream);
 
 /* ---- prototype updates ------------------------------------------------------ */
 /* ma(): P_k <- P_k*rho_k + (1-rho_k)*sum_k/max(cnt_k,1), rho_k = lambda if cnt_k>0 else 1; same for the
@@ -214,11 +225,14 @@ int onda_allreduce_oneshot(float* out, size_t n, int rank, int world, void* cons
  * (onda_sums_floats(C, D) floats: the statistics tail is global afterwards).  Same slot / flag / epoch rules as
  * onda_allreduce_oneshot.  If epoch_counter (device, one uint32 per slot, initialised to the same non-zero value
  * on every rank) is given, the epoch is read from it and incremented by the kernel, and `epoch` is ignored: the
- * call can then be captured in a CUDA graph and replayed. */
+ * call can then be captured in a CUDA graph and replayed.  peer_done_host (or NULL): per rank r, the device pointer
+ * of r's "done" words; once this rank has read every slot it stores the epoch into done[r][rank] on every peer, which
+ * is what onda_pseudolabel_fused_guarded waits for before it overwrites a slot. */
 int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, const float* counter, float* sums_out,
                                         int C, int D, float ma_lambda, int metric, float* table, int rank, int world,
-                                        void* const* peer_bufs_host, void* const* peer_flags_host, uint32_t epoch,
-                                        uint32_t* epoch_counter, void* stream);
+                                        void* const* peer_bufs_host, void* const* peer_flags_host,
+                                        void* const* peer_done_host, uint32_t epoch, uint32_t* epoch_counter,
+                                        void* stream);
 
 #ifdef __cplusplus
 }

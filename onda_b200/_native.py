@@ -39,6 +39,8 @@ _SIGNATURES = {
     "onda_prototype_std": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p]),
     "onda_pseudolabel_fused": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                          _p, _p, _p, _p, _p, C.c_size_t, C.c_int, _p]),
+    "onda_pseudolabel_fused_guarded": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                 _p, _p, _p, _p, _p, C.c_size_t, C.c_int, _p, _p, C.c_int, _p]),
     "onda_ema_update": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_float, _p]),
     "onda_ema_update_and_table": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_float, C.c_int, _p, _p]),
     "onda_append_update": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, _p]),
@@ -52,7 +54,8 @@ _SIGNATURES = {
     "onda_allreduce_oneshot": (C.c_int, [_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(_p), C.POINTER(_p),
                                          C.c_uint32, _p]),
     "onda_ema_update_and_table_allreduce": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_float, C.c_int, _p,
-                                                      C.c_int, C.c_int, C.POINTER(_p), C.POINTER(_p), C.c_uint32, _p, _p]),
+                                                      C.c_int, C.c_int, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p),
+                                                      C.c_uint32, _p, _p]),
 }
 
 

@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
             if (gather && epoch_counter != nullptr) *epoch_counter = epoch + 1u;     // every CTA has read it by now
         }
     }
+    if (last_flag && gather) peer_publish_done(peers, rank, world, epoch);          // every CTA's peer reads are complete
 }
 
 __global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
@@ -273,8 +274,19 @@ __global__ void class_std_kernel(const float* __restrict__ P, const float* __res
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ cta_partials, int n_cta,
                                                               size_t stride, int class_elems, int has_sums,
                                                               const float* __restrict__ stat_partials, int n_stat,
-                                                              int has_stats, float* __restrict__ out) {
+                                                              int has_stats, float* __restrict__ out,
+                                                              const uint32_t* __restrict__ peer_done,
+                                                              const uint32_t* __restrict__ peer_epoch, int peer_world) {
     __shared__ double part[8][32];
+    if (peer_done != nullptr && threadIdx.x == 0) {      // `out` is peer-visible: its previous contents must have been read
+        const uint32_t want = *peer_epoch - 1u;
+        unsigned spins = 0;
+        for (int r = 0; r < peer_world; ++r)
+            while ((int)(ld_acquire_sys(peer_done + r) - want) < 0) {
+                __nanosleep(200);
+                if (++spins > 200000000u) __trap();
+            }
+    }
     const int el = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + el;
     const int total = class_elems + kStatSlots;
@@ -762,7 +774,18 @@ int onda_prototype_std(const float* prototypes, const float* squared_mean, int C
 int onda_pseudolabel_fused(const float* feat, const float* prior, const float* logits, const float* table, int B, int D,
                            int HW, int C, float tau, float thresh, int64_t* labels, float* soft, float* dist,
                            float* sums, void* workspace, size_t workspace_bytes, int impl, void* stream_) {
+    return onda_pseudolabel_fused_guarded(feat, prior, logits, table, B, D, HW, C, tau, thresh, labels, soft, dist, sums,
+                                          workspace, workspace_bytes, impl, nullptr, nullptr, 0, stream_);
+}
+
+int onda_pseudolabel_fused_guarded(const float* feat, const float* prior, const float* logits, const float* table, int B,
+                                   int D, int HW, int C, float tau, float thresh, int64_t* labels, float* soft,
+                                   float* dist, float* sums, void* workspace, size_t workspace_bytes, int impl,
+                                   const uint32_t* peer_done, const uint32_t* peer_epoch, int peer_world,
+                                   void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    ONDA_REQUIRE((peer_done == nullptr) == (peer_epoch == nullptr) && peer_world >= 0 && peer_world <= kMaxPeers,
+                 "onda_pseudolabel_fused_guarded: bad peer guard");
     ONDA_REQUIRE(feat && sums && workspace, "onda_pseudolabel_fused: null feat/sums/workspace");
     ONDA_REQUIRE(B > 0 && D > 0 && HW > 0, "onda_pseudolabel_fused: empty shape B=%d D=%d HW=%d", B, D, HW);
     ONDA_REQUIRE(C > 0 && C <= ONDA_MAX_CLASSES, "onda_pseudolabel_fused: %d classes unsupported (max %d)", C,
@@ -818,7 +841,8 @@ int onda_pseudolabel_fused(const float* feat, const float* prior, const float* l
     const int class_elems = 2 * C * D + C;
     const int blocks = (class_elems + kStatSlots + 31) / 32;
     reduce_partials_kernel<<<blocks, 256, 0, stream>>>(p.cta_partials, n_cta, sums_floats(C, D), class_elems,
-                                                       want_sums ? 1 : 0, p.stat_partials, n_stat, want_dist ? 1 : 0, sums);
+                                                       want_sums ? 1 : 0, p.stat_partials, n_stat, want_dist ? 1 : 0, sums,
+                                                       peer_done, peer_epoch, peer_world);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
@@ -850,8 +874,9 @@ int onda_ema_update_and_table(float* prototypes, float* squared_mean, const floa
 
 int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, const float* counter, float* sums_out,
                                         int C, int D, float ma_lambda, int metric, float* table, int rank, int world,
-                                        void* const* peer_bufs_host, void* const* peer_flags_host, uint32_t epoch,
-                                        uint32_t* epoch_counter, void* stream) {
+                                        void* const* peer_bufs_host, void* const* peer_flags_host,
+                                        void* const* peer_done_host, uint32_t epoch, uint32_t* epoch_counter,
+                                        void* stream) {
     ONDA_REQUIRE(prototypes && squared_mean && sums_out && table && peer_bufs_host && peer_flags_host,
                  "onda_ema_update_and_table_allreduce: null pointer");
     ONDA_REQUIRE(C > 0 && C <= ONDA_MAX_CLASSES && D > 0, "onda_ema_update_and_table_allreduce: unsupported shape C=%d D=%d", C, D);
@@ -862,7 +887,7 @@ int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, 
     ONDA_REQUIRE(epoch != 0 || epoch_counter, "onda_ema_update_and_table_allreduce: epoch 0 is the flags' initial value");
     for (int r = 0; r < world; ++r)
         ONDA_REQUIRE(peer_bufs_host[r] && peer_flags_host[r], "onda_ema_update_and_table_allreduce: null peer pointer for rank %d", r);
-    const PeerTable peers = make_peer_table(rank, world, peer_bufs_host, peer_flags_host);
+    const PeerTable peers = make_peer_table(rank, world, peer_bufs_host, peer_flags_host, peer_done_host);
     table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
                                                                                    table, nullptr, ma_lambda, peers, rank, world, epoch, sums_out, epoch_counter);
     ONDA_CUDA_TRY(cudaGetLastError());

@@ -84,7 +84,9 @@ constexpr int kMaxPeers = 8;
 struct PeerTable {
     const float* buf[kMaxPeers];      // rank r's input slot, mapped into this process
     uint32_t* flags[kMaxPeers];       // rank r's flag words for this slot: flags[r][src] = epoch when src is ready
+    uint32_t* done[kMaxPeers];        // rank r's "done" words (or null): done[r][src] = epoch once src has read r's slot
 };
+constexpr long long kPeerSpinLimit = 200000000LL;      // probes 256 ns apart: about a minute, then the kernel traps
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -100,13 +102,22 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
     return v;
 }
 
-inline PeerTable make_peer_table(int rank, int world, void* const* bufs, void* const* flags) {
+inline PeerTable make_peer_table(int rank, int world, void* const* bufs, void* const* flags, void* const* done = nullptr) {
     PeerTable t;
     for (int r = 0; r < kMaxPeers; ++r) {
         t.buf[r] = (const float*)bufs[r < world ? r : rank];    // unused entries stay dereferenceable and local (peer_gather4)
         t.flags[r] = r < world ? (uint32_t*)flags[r] : nullptr;
+        t.done[r] = (r < world && done != nullptr) ? (uint32_t*)done[r] : nullptr;
     }
     return t;
+}
+// After the last read of the peers' slots: tell every peer "rank has read your slot of this epoch".  One thread per peer.
+__device__ __forceinline__ void peer_publish_done(const PeerTable& peers, int rank, int world, uint32_t epoch) {
+    uint32_t* done_of_peer = nullptr;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (r == (int)threadIdx.x) done_of_peer = peers.done[r];
+    if ((int)threadIdx.x < world && done_of_peer != nullptr) st_release_sys(done_of_peer + rank, epoch);
 }
 // Handshake of a one-shot exchange: publish "my input is ready" (epoch) on every peer, wait for all peers'.
 // Called by every thread of every CTA; CTA 0 publishes.  Ends with __syncthreads().
@@ -126,9 +137,9 @@ __device__ __forceinline__ void peer_handshake(const PeerTable& peers, int rank,
     if ((int)threadIdx.x < world) {
         const uint32_t* mine = my_flags + threadIdx.x;
         long long spins = 0;
-        while (ld_acquire_sys(mine) != epoch) {
-            __nanosleep(64);
-            if (++spins > 40000000LL) __trap();                   // a missing peer traps instead of hanging the GPU
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {         // epochs only grow: a later one also means "ready"
+            __nanosleep(256);
+            if (++spins > kPeerSpinLimit) __trap();               // a missing peer traps instead of hanging the GPU
         }
     }
     __syncthreads();

@@ -176,7 +176,9 @@ __device__ __forceinline__ void rectify_pixel(float (&v)[CP], const float (&pri)
         }
     }
     entropy = -entropy / log2f((float)C);
-    if (rsum != rsum) { best = rsum; arg = 0; }            // torch.max on a NaN row: value NaN, first index
+    // torch.max on a NaN row: value NaN, first index.  A row whose rectified sum is exactly zero (q * prior underflowed
+    // for every class) is such a row in the reference too (0 / 0), so it keeps label 0 and a NaN posterior.
+    if (rsum != rsum || rsum == 0.f) { best = __int_as_float(0x7fc00000); arg = 0; }
     m_out = best;
     label = (best < thresh) ? ONDA_IGNORE_LABEL : arg;
 }

@@ -71,9 +71,10 @@ class WeightEma:
     def update(self, ema_update):
         keep = float(ema_update)
         take = 1.0 - keep                              # computed in double like the reference, rounded to fp32 by the call
-        stream = nat.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        nat.check(self._lib.onda_weight_ema_update(nat.ptr(self._table), self.n_chunks, keep, take, stream),
-                  "onda_weight_ema_update")
+        with torch.cuda.device(self.device):          # the C ABI launches on the current device
+            stream = nat.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            nat.check(self._lib.onda_weight_ema_update(nat.ptr(self._table), self.n_chunks, keep, take, stream),
+                      "onda_weight_ema_update")
 
 
 _cache = {}

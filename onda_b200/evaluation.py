@@ -45,9 +45,10 @@ class ConfusionMeter:
         B, C, h, w = pred.shape
         _, H, W = lab.shape
         out = torch.empty((B, H, W), dtype=torch.uint8, device=pred.device) if return_prediction else None
-        stream = nat.C.c_void_p(torch.cuda.current_stream(pred.device).cuda_stream)
-        nat.check(self._lib.onda_confusion_update(nat.ptr(pred), B, C, h, w, nat.ptr(lab), H, W, nat.ptr(self._hist),
-                                                  nat.ptr(out), stream), "onda_confusion_update")
+        with torch.cuda.device(pred.device):          # the C ABI launches on the current device
+            stream = nat.C.c_void_p(torch.cuda.current_stream(pred.device).cuda_stream)
+            nat.check(self._lib.onda_confusion_update(nat.ptr(pred), B, C, h, w, nat.ptr(lab), H, W, nat.ptr(self._hist),
+                                                      nat.ptr(out), stream), "onda_confusion_update")
         return out
 
     def hist(self):

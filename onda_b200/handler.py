@@ -31,6 +31,12 @@ def _stream_ptr(device):
     return nat.C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _on(device):
+    """The C ABI launches on the CURRENT device: make the tensors' device current for the duration of the calls (the
+    handler may live on cuda:1, or be used from a process that never called torch.cuda.set_device)."""
+    return torch.cuda.device(device)
+
+
 class _CpuUnpickler(pickle.Unpickler):
     """pickle.load for tensors that were saved from a CUDA device, on a machine without one."""
 
@@ -104,8 +110,8 @@ class prototype_handler:
         """Load the 3-tuple written by ``save``; returns False if the file is absent (:40-47).
 
         Also reads the legacy 2-tuple ``(prototypes, counter)`` of the ``prototypes.pickle`` shipped with the
-        reference (which the reference's own ``load`` cannot unpack): ``squared_mean`` then stays uninitialised, so
-        only the Euclidean metric works until ``append`` has rebuilt the state.  Tensors pickled on a CUDA device are
+        reference (which the reference's own ``load`` cannot unpack): ``squared_mean`` then stays uninitialised (only
+        the Euclidean metric works) until the first ``append``, which starts the second moments from zero.  Tensors pickled on a CUDA device are
         mapped to the CPU when no CUDA device is present.
         """
         if os.path.exists(loc):
@@ -196,9 +202,10 @@ class prototype_handler:
         if hit is not None and hit[0] == key:
             return hit[1]
         table = self._buf(("table", metric), (self._lib.onda_table_floats(C, D),), torch.float32, device, zero=True)
-        nat.check(self._lib.onda_build_distance_table(
-            nat.ptr(P), nat.ptr(S) if need_stats else None, nat.ptr(cnt) if need_stats else None,
-            C, D, nat.METRIC[metric], nat.ptr(table), _stream_ptr(device)), "onda_build_distance_table")
+        with _on(device):
+            nat.check(self._lib.onda_build_distance_table(
+                nat.ptr(P), nat.ptr(S) if need_stats else None, nat.ptr(cnt) if need_stats else None,
+                C, D, nat.METRIC[metric], nat.ptr(table), _stream_ptr(device)), "onda_build_distance_table")
         self._table[metric] = (key, table)
         return table
 
@@ -213,18 +220,21 @@ class prototype_handler:
         soft = torch.empty((N, C), dtype=torch.float32, device=device) if want_soft else None
         dist = torch.empty((N, C), dtype=torch.float32, device=device) if want_dist else None
         n_sums = self._lib.onda_sums_floats(C, D)
-        sums = None
+        sums, guard = None, (None, None, 0)
         if self.process_group is not None and self.allreduce == "oneshot" and logits3 is not None:
             sums = self._symm_slot(n_sums, device)      # written straight into peer-visible memory: no staging copy
+            if sums is not None:                        # ... once the peers have read what it held (their "done" words)
+                guard = self._symm[4][self._ar_calls & 1][4]
         if sums is None:
             sums = torch.empty((n_sums,), dtype=torch.float32, device=device)
         impl = nat.IMPL[self.impl]
-        wbytes = self._lib.onda_fused_workspace_bytes(B, D, HW, C, impl)
-        work = self._buf("work", (wbytes,), torch.uint8, device)
-        nat.check(self._lib.onda_pseudolabel_fused(
-            nat.ptr(feat3), nat.ptr(prior3), nat.ptr(logits3), nat.ptr(table), B, D, HW, C,
-            float(self.tau), float(self.thresh), nat.ptr(labels), nat.ptr(soft), nat.ptr(dist), nat.ptr(sums),
-            nat.ptr(work), wbytes, impl, _stream_ptr(device)), "onda_pseudolabel_fused")
+        with _on(device):
+            wbytes = self._lib.onda_fused_workspace_bytes(B, D, HW, C, impl)
+            work = self._buf("work", (wbytes,), torch.uint8, device)
+            nat.check(self._lib.onda_pseudolabel_fused_guarded(
+                nat.ptr(feat3), nat.ptr(prior3), nat.ptr(logits3), nat.ptr(table), B, D, HW, C,
+                float(self.tau), float(self.thresh), nat.ptr(labels), nat.ptr(soft), nat.ptr(dist), nat.ptr(sums),
+                nat.ptr(work), wbytes, impl, guard[0], guard[1], guard[2], _stream_ptr(device)), "onda_pseudolabel_fused")
         return labels, soft, dist, sums
 
     def _num_classes(self, other=None):
@@ -238,8 +248,9 @@ class prototype_handler:
         self._require_cuda(self.prototypes, "prototypes")
         P, S, _ = self._state(self.prototypes.device, True)
         out = torch.empty_like(P)
-        nat.check(self._lib.onda_prototype_std(nat.ptr(P), nat.ptr(S), P.shape[0], P.shape[1], nat.ptr(out),
-                                               _stream_ptr(P.device)), "onda_prototype_std")
+        with _on(P.device):
+            nat.check(self._lib.onda_prototype_std(nat.ptr(P), nat.ptr(S), P.shape[0], P.shape[1], nat.ptr(out),
+                                                   _stream_ptr(P.device)), "onda_prototype_std")
         return out
 
     def global_var(self):
@@ -249,8 +260,9 @@ class prototype_handler:
         table = self._distance_table("mahalanobis", device)
         C, D = self.prototypes.shape
         out = torch.empty((D,), dtype=torch.float32, device=device)
-        nat.check(self._lib.onda_table_global_std(nat.ptr(table), C, D, nat.ptr(out), _stream_ptr(device)),
-                  "onda_table_global_std")
+        with _on(device):
+            nat.check(self._lib.onda_table_global_std(nat.ptr(table), C, D, nat.ptr(out), _stream_ptr(device)),
+                      "onda_table_global_std")
         return out
 
     # ------------------------------------------------------------------ distances
@@ -287,7 +299,9 @@ class prototype_handler:
     @property
     def last_stats(self):
         """Batch statistics of the most recent fused pass (means over all pixels; over all ranks
-        once ``ma`` has all-reduced them).  Read lazily: the device-to-host copy happens here."""
+        once ``ma`` has all-reduced them).  Read lazily: the device-to-host copy happens here, so read it before the
+        next-but-one fused pass -- the device buffer behind it (one of two alternating ones when the ranks exchange
+        through peer memory) is reused then."""
         src = self._stats_src
         if src is not None and self._stats_cache is None:
             self._stats_cache = self._stats_from(*src)
@@ -332,6 +346,13 @@ class prototype_handler:
                 import torch.distributed as dist
                 dist.all_reduce(sums[2 * C * D + C:], op=dist.ReduceOp.SUM, group=self.process_group)
             self._monitor_side_effects(confidence_monitor, self.last_stats)
+            if self.tau != tau_used and want_soft:
+                # the confidence regulariser raised tau (prototype_handler.py:151-156): the reference's soft call that
+                # follows the hard one already sees the new value, so the soft predictions are recomputed with it
+                stats_keep = (self._stats_src, self._stats_cache)
+                _, soft, _, _ = self._launch(feat3, prior3, None, self.distance_metric, False, True, False, C)
+                self._stats_src, self._stats_cache = stats_keep
+                tau_used = self.tau
         self._memo = (weakref.ref(feat), feat._version, weakref.ref(prior), prior._version, self._epoch,
                       tau_used, self.thresh, labels, soft, sums)
         return labels, soft
@@ -384,9 +405,11 @@ class prototype_handler:
         device = ref.device
         prior = torch.empty((B, C, HW), dtype=torch.float32, device=device) if write_prior else None
         stats = torch.empty((nat.NUM_STATS,), dtype=torch.float32, device=device)
-        wbytes = self._lib.onda_prior_workspace_bytes(B, C, HW)
+        with _on(device):
+            wbytes = self._lib.onda_prior_workspace_bytes(B, C, HW)
         work = self._buf("prior_work", (wbytes,), torch.uint8, device, zero=True)
-        nat.check(self._lib.onda_prior_mix_stats(
+        with _on(device):
+          nat.check(self._lib.onda_prior_mix_stats(
             nat.ptr(dense[0]), nat.ptr(dense[1]), nat.ptr(dense[2]), float(coefs[0]), float(coefs[1]), float(coefs[2]),
             float(scale01), B, C, HW, nat.ptr(prior), nat.ptr(stats), nat.ptr(work), wbytes, _stream_ptr(device)), "onda_prior_mix_stats")
         if self.process_group is not None:
@@ -417,11 +440,12 @@ class prototype_handler:
         P, _, _ = self._state(device, False)
         labels = pseudolabels.contiguous()
         out4 = torch.empty((4,), dtype=torch.float32, device=device)
-        wbytes = self._lib.onda_step_log_workspace_bytes()
-        work = self._buf("log_work", (wbytes,), torch.uint8, device, zero=True)
-        nat.check(self._lib.onda_step_log_stats(nat.ptr(labels), nat.ptr(logits3), nat.ptr(P), B, C, HW, P.shape[1],
-                                                nat.ptr(out4), nat.ptr(work), wbytes, _stream_ptr(device)),
-                  "onda_step_log_stats")
+        with _on(device):
+            wbytes = self._lib.onda_step_log_workspace_bytes()
+            work = self._buf("log_work", (wbytes,), torch.uint8, device, zero=True)
+            nat.check(self._lib.onda_step_log_stats(nat.ptr(labels), nat.ptr(logits3), nat.ptr(P), B, C, HW, P.shape[1],
+                                                    nat.ptr(out4), nat.ptr(work), wbytes, _stream_ptr(device)),
+                      "onda_step_log_stats")
         if self.process_group is not None:
             import torch.distributed as dist
             keep = out4[2].clone()                   # the prototypes are replicated, not sharded
@@ -478,18 +502,22 @@ class prototype_handler:
         peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
         # per slot: (view of this rank's input, peers' input pointers, peers' flag pointers) -- built once, the step
         # itself must not spend host time on it
+        # epochs of the exchange fused into ma(): one device counter per slot, bumped by the kernel itself, so the
+        # call has no per-step host argument and can be replayed from a CUDA graph
+        self._epoch_ctr = torch.ones((2,), dtype=torch.int32, device=device)
         slots = []
         for slot in (0, 1):
             view = buf[slot * slot_floats: slot * slot_floats + n]
             bufs = ptr_t(*[p + 4 * slot * slot_floats for p in peer_ptrs])
             flags = ptr_t(*[p + 4 * (2 * slot_floats + 32 * slot) for p in peer_ptrs])
             flags_fused = ptr_t(*[p + 4 * (2 * slot_floats + 32 * slot + 8) for p in peer_ptrs])   # own words: own epochs
-            slots.append((view, bufs, flags, flags_fused))
+            done = ptr_t(*[p + 4 * (2 * slot_floats + 32 * slot + 16) for p in peer_ptrs])         # "has read my slot" words
+            # the writer's guard: this rank's own done words, the slot's epoch counter, the number of ranks
+            guard = (nat.C.c_void_p(peer_ptrs[rank] + 4 * (2 * slot_floats + 32 * slot + 16)),
+                     nat.C.c_void_p(self._epoch_ctr.data_ptr() + 4 * slot), world)
+            slots.append((view, bufs, flags, flags_fused, guard, done))
         self._symm = (buf, hdl, n, slot_floats, slots, rank, world)
         self._ar_calls = 0
-        # epochs of the exchange fused into ma(): one device counter per slot, bumped by the kernel itself, so the
-        # call has no per-step host argument and can be replayed from a CUDA graph
-        self._epoch_ctr = torch.ones((2,), dtype=torch.int32, device=device)
 
     def _symm_slot(self, n, device):
         """The peer-visible input slot of the next one-shot all-reduce (two slots, alternating per call)."""
@@ -512,12 +540,12 @@ class prototype_handler:
             return None
         _, _, _, _, slots, rank, world = self._symm
         slot = self._ar_calls & 1
-        _, bufs, flags, flags_fused = slots[slot]
+        _, bufs, flags, flags_fused, _, done = slots[slot]
         if sums.data_ptr() != slot_view.data_ptr():
             slot_view.copy_(sums)                       # input was produced elsewhere: stage it
         self._ar_calls += 1
         if fused:
-            return rank, world, bufs, flags_fused, self._epoch_ctr.data_ptr() + 4 * slot
+            return rank, world, bufs, flags_fused, (done, self._epoch_ctr.data_ptr() + 4 * slot)
         return rank, world, bufs, flags, self._ar_calls
 
     def _allreduce_oneshot(self, sums):
@@ -529,8 +557,9 @@ class prototype_handler:
         rank, world, bufs, flags, epoch = args
         n = sums.numel()
         out = torch.empty((n,), dtype=torch.float32, device=sums.device)
-        nat.check(self._lib.onda_allreduce_oneshot(nat.ptr(out), n, rank, world, bufs, flags, epoch,
-                                                   _stream_ptr(sums.device)), "onda_allreduce_oneshot")
+        with _on(sums.device):
+            nat.check(self._lib.onda_allreduce_oneshot(nat.ptr(out), n, rank, world, bufs, flags, epoch,
+                                                       _stream_ptr(sums.device)), "onda_allreduce_oneshot")
         return out
 
     def get_proto_array(self, feat, out):
@@ -556,12 +585,13 @@ class prototype_handler:
         fused_exchange = args is not None
         if fused_exchange:
             # all-reduce + blend + next distance table in ONE launch: the kernel reads the peers' slots over NVLink
-            rank, world, bufs, flags, epoch_ctr = args
+            rank, world, bufs, flags, (done, epoch_ctr) = args
             reduced = self._buf(("reduced", self._ar_calls & 1), (sums.numel(),), torch.float32, device)
             table = self._buf(("table", metric), (self._lib.onda_table_floats(C, D),), torch.float32, device, zero=True)
-            nat.check(self._lib.onda_ema_update_and_table_allreduce(
+            with _on(device):
+              nat.check(self._lib.onda_ema_update_and_table_allreduce(
                 nat.ptr(P), nat.ptr(S), nat.ptr(cnt) if need_stats else None, nat.ptr(reduced), C, D,
-                float(self.ma_lambda), nat.METRIC[metric], nat.ptr(table), rank, world, bufs, flags, 0, epoch_ctr,
+                float(self.ma_lambda), nat.METRIC[metric], nat.ptr(table), rank, world, bufs, flags, done, 0, epoch_ctr,
                 _stream_ptr(device)), "onda_ema_update_and_table_allreduce")
             sums = reduced
         else:
@@ -576,15 +606,17 @@ class prototype_handler:
             self._table = {metric: (self._table_key(P, S, cnt, need_stats, device), table)}
             return
         if need_stats and cnt is None:
-            nat.check(self._lib.onda_ema_update(nat.ptr(P), nat.ptr(S), nat.ptr(sums), C, D, float(self.ma_lambda),
-                                                _stream_ptr(device)), "onda_ema_update")
+            with _on(device):
+                nat.check(self._lib.onda_ema_update(nat.ptr(P), nat.ptr(S), nat.ptr(sums), C, D, float(self.ma_lambda),
+                                                    _stream_ptr(device)), "onda_ema_update")
             self._epoch += 1
             return
         # blend and rebuild the distance table for the next step in one launch
         table = self._buf(("table", metric), (self._lib.onda_table_floats(C, D),), torch.float32, device, zero=True)
-        nat.check(self._lib.onda_ema_update_and_table(
-            nat.ptr(P), nat.ptr(S), nat.ptr(cnt) if need_stats else None, nat.ptr(sums), C, D, float(self.ma_lambda),
-            nat.METRIC[metric], nat.ptr(table), _stream_ptr(device)), "onda_ema_update_and_table")
+        with _on(device):
+            nat.check(self._lib.onda_ema_update_and_table(
+                nat.ptr(P), nat.ptr(S), nat.ptr(cnt) if need_stats else None, nat.ptr(sums), C, D, float(self.ma_lambda),
+                nat.METRIC[metric], nat.ptr(table), _stream_ptr(device)), "onda_ema_update_and_table")
         self._epoch += 1
         self._table = {metric: (self._table_key(P, S, cnt, need_stats, device), table)}
 
@@ -595,11 +627,14 @@ class prototype_handler:
         if isinstance(self.prototypes, int):     # first call allocates the state (:68-70)
             self.prototypes = torch.zeros((C, D), dtype=torch.float32, device=device)
             self.squared_mean = torch.zeros((C, D), dtype=torch.float32, device=device)
+        if not isinstance(self.squared_mean, torch.Tensor):     # state loaded from the legacy 2-tuple pickle: no second moments yet
+            self.squared_mean = torch.zeros((C, D), dtype=torch.float32, device=device)
         if not isinstance(self.counter, torch.Tensor):
             self.counter = torch.full((C,), float(self.counter), dtype=torch.float32, device=device)
         P, S, cnt = self._state(device, True)
         if P.shape != (C, D):
             raise ValueError(f"feat/out give a {C}x{D} update but prototypes are {tuple(P.shape)}")
-        nat.check(self._lib.onda_append_update(nat.ptr(P), nat.ptr(S), nat.ptr(cnt), nat.ptr(sums), C, D,
-                                               _stream_ptr(device)), "onda_append_update")
+        with _on(device):
+            nat.check(self._lib.onda_append_update(nat.ptr(P), nat.ptr(S), nat.ptr(cnt), nat.ptr(sums), C, D,
+                                                   _stream_ptr(device)), "onda_append_update")
         self._epoch += 1

@@ -531,6 +531,40 @@ def test_tau_regularisation_side_effect():
     assert h.tau == pytest.approx(1.001)                        # frozen monitor: no side effects
 
 
+def test_fused_call_follows_the_tau_bump_like_two_reference_calls():
+    """With the confidence regulariser firing, the reference's hard call raises tau and its soft call that follows
+    already uses the new value (prototype_handler.py:151-156): pseudo_labels_fused must return that pair."""
+    from onda_b200 import Monitor
+    case = po.synth_case(53, 1, 32, 6, 9)
+    h = make_handler(case["protos"], case["sq_mean"], case["counter"], "mahalanobis")
+    orc = make_oracle(case["protos"], case["sq_mean"], case["counter"], "mahalanobis")
+    h.confidence_regularization_threshold = orc.confidence_regularization_threshold = 0.0
+    mon, omon = Monitor(10), po.OracleMonitor(10)
+    feat, prior = case["feat"].to(dev()), case["prior"].to(dev())
+    ref_labels = orc.pseudo_labels(case["feat"], case["prior"], confidence_monitor=omon)
+    ref_soft = orc.pseudo_labels(case["feat"], case["prior"], soft=True)
+    labels, soft = h.pseudo_labels_fused(feat, prior, None, confidence_monitor=mon)
+    assert h.tau == pytest.approx(1.001) and orc.tau == pytest.approx(1.001)
+    assert float((soft.cpu() - ref_soft).abs().max()) <= 1e-5
+    check_labels(labels, ref_labels, po.rectify(orc.distance_measure(case["feat"]), po.to_rows(case["prior"]), 1.0)[1], np.float32(0.3))
+
+
+def test_zero_rectified_row_keeps_label_zero_like_the_reference():
+    """A pixel whose prior is zero for every class: the reference divides 0 / 0, gets a NaN row, and torch.max returns
+    (NaN, index 0), which is not below the threshold -> label 0 (prototype_handler.py:159-166)."""
+    case = po.synth_case(54, 1, 32, 4, 5)
+    case["prior"][0, :, 1, 2] = 0.0
+    h = make_handler(case["protos"], case["sq_mean"], case["counter"], "mahalanobis")
+    orc = make_oracle(case["protos"], case["sq_mean"], case["counter"], "mahalanobis")
+    ref_labels, ref_soft = po.fused_step(orc, case["feat"], case["prior"], case["out"])
+    labels, soft = h.pseudo_labels_fused(case["feat"].to(dev()), case["prior"].to(dev()), case["out"].to(dev()))
+    n = 1 * 5 + 2
+    assert int(ref_labels[n]) == 0 and bool(torch.isnan(ref_soft[n]).all())
+    assert int(labels[n]) == 0 and bool(torch.isnan(soft[n]).all())
+    ok = torch.ones(ref_labels.numel(), dtype=torch.bool); ok[n] = False
+    assert float((soft.cpu()[ok] - ref_soft[ok]).abs().max()) <= 1e-5
+
+
 LABEL_MAPS = ["one_class", "two_classes_odd_split", "aligned_runs_of_32", "stripes_of_5", "random", "ragged_tail"]
 
 

@@ -78,7 +78,7 @@ def test_sharded_matches_single_gpu(mode):
     assert float((single != sharded).float().mean()) < 1e-3
 
 
-def _graph_worker(rank, world, port, ret):
+def _graph_worker(rank, world, port, n_graphs, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -105,17 +105,21 @@ def _graph_worker(rank, world, port, ret):
             step(0), step(1)                                  # 2 eager steps (buffers, symmetric memory)
             if use_graph:
                 graphs = []
-                for k in range(2):                            # capture also runs nothing: 2 + 6 replayed steps
+                for k in range(n_graphs):                     # capture also runs nothing: 2 + 6 replayed steps
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         step(k)
                     graphs.append(g)
                 dist.barrier()
                 for i in range(6):
-                    graphs[i % 2].replay()
+                    graphs[i % n_graphs].replay()
+                    if rank == 0 and i == 2:
+                        torch.cuda.synchronize()              # rank skew: rank 1 runs ahead as far as the protocol lets it
+                        import time
+                        time.sleep(0.2)
             else:
                 for i in range(6):
-                    step(i % 2)
+                    step(i % n_graphs)
             torch.cuda.synchronize()
             dist.barrier()
             results.append((h.prototypes.cpu().clone(), h.squared_mean.cpu().clone()))
@@ -124,15 +128,18 @@ def _graph_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_graph_replayed_steps_equal_eager_steps():
-    """The exchange fused into ma() keeps its epoch in device memory: captured once per slot, a step can be replayed from
-    a CUDA graph.  Eight steps (two eager + six replayed) give bit-identical prototypes to eight eager steps, on every rank."""
+@pytest.mark.parametrize("n_graphs", [2, 1])
+def test_graph_replayed_steps_equal_eager_steps(n_graphs):
+    """The exchange fused into ma() keeps its epoch in device memory and the writer of a peer-visible slot waits for the
+    peers' "done" words, so a step can be replayed from a CUDA graph -- two graphs alternating over the two slots, or ONE
+    graph that reuses a single slot every step (with one rank deliberately delayed).  Eight steps (two eager + six
+    replayed) give bit-identical prototypes to eight eager steps, on every rank."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_graph_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    mp.spawn(_graph_worker, args=(world, _free_port(), n_graphs, ret), nprocs=world, join=True)
     for r in range(world):
         (pe, se), (pg, sg) = ret[r]
         assert torch.equal(pe, pg) and torch.equal(se, sg)
