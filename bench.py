@@ -2,6 +2,7 @@
 """Benchmark of the prototype pseudo-labelling hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl onda|reference] [--d 256|2048]
+                    [--scaling weak|strong] [--batch B]
 
 One *step* = the fused pass over one batch of synthetic, Cityscapes-shaped input: hard
 pseudo-labels + soft predictions + per-class feature sum / sum of squares / count + batch
@@ -9,15 +10,18 @@ confidence statistics, followed by the EMA prototype update -- what the referenc
 ``pseudo_labels`` x2 + ``ma`` (prototypes_hybrid_switch.py:89-93, prototypes.py:292-294).
 
 Workload (config.workload): BASELINE.json configs[2], the batch-sharded prototype path at
-1024x512 (65x129 stride-8 map), 19 classes, mahalanobis, hybrid_switch.yml parameters, with
-B=32 images PER GPU (weak scaling: every rank keeps 32 images; the only collective is the
-all-reduce of the 19x(2D+1)+8 class-sum/statistics buffer before the EMA update).
+1024x512 (65x129 stride-8 map), 19 classes, mahalanobis, hybrid_switch.yml parameters.
+``--scaling weak`` (default): B=32 images PER GPU, every rank keeps 32 images as N grows;
+``--scaling strong``: B=32 images IN TOTAL, 32/N per rank (the split BASELINE configs[2] names).
+The only collective is the exchange of the 19x(2D+1)+8 class-sum/statistics buffer before the
+EMA update.
 
 Printed (rank 0, one JSON line): ``value`` = pixels/s over all ranks with inputs resident in
 HBM; ``e2e`` = the same through the public API from pinned HOST buffers (H2D of feat/prior/out
-and D2H of labels + statistics inside the timed region); ``roofline`` for the dominant kernel
-(algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json); ``cpu_baseline`` = the oracle
-port of the reference timed on this box's host cores on a bounded sample.
+and D2H of labels + soft predictions + statistics inside the timed region); ``roofline`` for the
+dominant kernel (algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json); ``cpu_baseline``
+= the reference's own prototype_handler (oracle/_ref, staged by ``__graft_entry__.build()``; the
+oracle port if that file is absent) timed on this box's host cores on the same batch.
 """
 from __future__ import annotations
 
@@ -50,7 +54,7 @@ def algorithmic_bytes_per_pixel(d):
 def measured_traffic(d):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if it does not apply)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_tc_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_tc_traffic.json")) as f:
             t = json.load(f)
         if d == 256:
             return t["dram_bytes_read"] + t["dram_bytes_write"]
@@ -131,51 +135,125 @@ def gpu_inputs(torch, device, d, n_sets, seed, block=8, margin=4.0):
 
 
 def cpu_reference_rate(torch, d, images, steps, warmup, threads):
-    """Times the oracle port of the reference (pseudo_labels hard + soft + ma) on host cores."""
+    """Times the reference path (pseudo_labels hard + soft + ma) on host cores: the reference's own prototype_handler
+    when ``oracle/_ref`` holds it (kind "reference"), else the oracle port (kind "port").  Returns (pixels per step,
+    list of step times, kind)."""
     from oracle import proto_oracle as po
+    from oracle.build_ref import load_reference_handler
     torch.set_num_threads(threads)
     case = po.synth_case(1234, images, d, H, W)
-    h = po.OracleHandler(**PARAMS)
+    ref_cls = load_reference_handler()
+    if ref_cls is not None:
+        h = ref_cls(ma_lambda=PARAMS["ma_lambda"], tau=PARAMS["tau"], thresh=PARAMS["thresh"],
+                    distance_metric=PARAMS["distance_metric"])
+        kind = "reference"
+
+        def one_step():
+            h.pseudo_labels(case["feat"], case["prior"])
+            h.pseudo_labels(case["feat"], case["prior"], soft=True)
+            h.ma(case["feat"], case["out"])
+    else:
+        h = po.OracleHandler(**PARAMS)
+        kind = "port"
+
+        def one_step():
+            po.fused_step(h, case["feat"], case["prior"], case["out"])
     h.prototypes, h.squared_mean, h.counter = case["protos"].clone(), case["sq_mean"].clone(), case["counter"].clone()
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        po.fused_step(h, case["feat"], case["prior"], case["out"])
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return images * H * W, times
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            one_step()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return images * H * W, times, kind
+
+
+def per_rank_images(args, world):
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit(f"--scaling strong needs --batch ({args.batch}) divisible by the number of GPUs ({world})")
+        return args.batch // world
+    return args.batch
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of one GPU's share of the step, all host threads."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    images = 4 if args.d <= 256 else 1
-    px, times = cpu_reference_rate(torch, args.d, images, args.steps, args.warmup, threads)
+    images = per_rank_images(args, args.gpus)
+    steps = max(1, min(args.steps, 8 if args.d <= 256 else 2))        # a full batch is ~1.4 s of CPU at D = 256
+    px, times, kind = cpu_reference_rate(torch, args.d, images, steps, 1, threads)
     dt = sum(times) / len(times)
     value = px / dt
-    sample = f"{images} of {B_PER_GPU} images per step ({px} px), oracle port of the reference torch path, {threads} threads"
+    what = "the reference's prototype_handler (oracle/_ref)" if kind == "reference" else "oracle port of the reference torch path"
+    sample = (f"one rank's full batch ({images} images, {px} px) per step, {steps} timed steps after 1 warm-up, {what}, "
+              f"{threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.d, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(args.d, args.gpus, args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(d, n_gpus, allreduce="oneshot"):
-    return {"workload": (f"BASELINE configs[2]: batch-sharded prototype path, B={B_PER_GPU} images per GPU at 1024x512 "
+def workload_config(d, n_gpus, args):
+    """Identical for both arms (the driver compares them)."""
+    b = per_rank_images(args, n_gpus)
+    split = (f"B={args.batch} images per GPU (weak scaling)" if args.scaling == "weak"
+             else f"B={args.batch} images in total, {b} per GPU (strong scaling)")
+    return {"workload": (f"BASELINE configs[2]: batch-sharded prototype path, {split} at 1024x512 "
                          f"(65x129 stride-8 map), D={d}, C={C}, mahalanobis, hybrid_switch.yml parameters; step = fused "
                          "hard+soft pseudo-labels + class sum/sumsq/count + statistics + EMA update"),
-            "B_per_gpu": B_PER_GPU, "D": d, "H": H, "W": W, "classes": C, "parallelism": f"batch-sharded x{n_gpus}",
-            "collective": f"{allreduce} all-reduce of 19x(2D+1)+8 floats per step" if n_gpus > 1 else "none",
-            "l2_policy": "inputs larger than L2 (338 MB per step at D=256) and two rotating input sets"}
+            "B_per_gpu": b, "D": d, "H": H, "W": W, "classes": C, "parallelism": f"batch-sharded x{n_gpus}",
+            "collective": "exchange of 19x(2D+1)+8 floats per step" if n_gpus > 1 else "none",
+            "l2_policy": "rotating input sets, together larger than twice the 126 MB L2 (two sets of 338 MB at B=32, D=256)"}
+
+
+def aux_kernel_numbers(torch, device):
+    """The widened rows, measured in the same run: model-weight EMA (one launch over a DeepLabV2-sized parameter set)
+    and the evaluation counters (upsample + argmax + confusion matrix of one 2048x1024 image)."""
+    from onda_b200 import WeightEma, ConfusionMeter
+    out = {}
+    try:
+        g = torch.Generator(device=device).manual_seed(3)
+        shapes = [(64, 3, 7, 7)] + [(256, 256, 3, 3)] * 60 + [(512,)] * 100 + [(2048, 512, 1, 1)] * 4
+        net = lambda: torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*sh, generator=g, device=device)) for sh in shapes])
+        q, k = net(), net()
+        plan = WeightEma(q, k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            plan.update(0.999)
+        e0.record()
+        for _ in range(10):
+            plan.update(0.999)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        n = sum(p.numel() for p in q)
+        out["weight_ema"] = {"params": n, "ms": ms, "gbs": 12 * n / (ms * 1e-3) / 1e9, "bytes_per_param": 12}
+        meter = ConfusionMeter(C)
+        pred = torch.randn(1, C, 129, 257, generator=g, device=device)
+        lab = torch.randint(0, C, (1, 1024, 2048), generator=g, device=device)
+        for _ in range(3):
+            meter.update(pred, lab)
+        e0.record()
+        for _ in range(10):
+            meter.update(pred, lab)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        out["confusion"] = {"full_res_pixels": 1024 * 2048, "ms": ms, "gpx_s": 1024 * 2048 / (ms * 1e-3) / 1e9}
+    except Exception as exc:                      # never let the side numbers break the bench line
+        out["error"] = repr(exc)
+    return out
 
 
 def run_onda(args):
@@ -196,10 +274,14 @@ def run_onda(args):
         dist.init_process_group("nccl", device_id=device)
         group = dist.group.WORLD
     d = args.d
+    globals()["B_PER_GPU"] = per_rank_images(args, world)
     N = B_PER_GPU * H * W
     lib = nat.load()
 
-    protos, sq_mean, counter, sets = gpu_inputs(torch, device, d, 2, 1234 + rank, block=args.label_block, margin=args.logit_margin)
+    # rotating input sets: together larger than twice the 126 MB L2, so no step finds its inputs cached
+    set_bytes = N * algorithmic_bytes_per_pixel(d)
+    n_sets = int(max(2, min(16, -(-2.2 * 126e6 // set_bytes))))
+    protos, sq_mean, counter, sets = gpu_inputs(torch, device, d, n_sets, 1234 + rank, block=args.label_block, margin=args.logit_margin)
     if world > 1:   # identical prototypes everywhere
         for t in (protos, sq_mean, counter):
             dist.broadcast(t, 0)
@@ -281,13 +363,52 @@ def run_onda(args):
     value = world * N * args.steps / (ms * 1e-3)
 
     # ---- end to end from pinned host buffers ------------------------------------------------
-    host = [tuple(x.cpu().pin_memory() for x in s) for s in sets]
-    dev_in = [tuple(torch.empty_like(x) for x in s) for s in sets]
+    # ---- multi-GPU correctness, visible to the driver: prototypes bit-identical on every rank, and the sharded result
+    # equal to one GPU running the concatenated shards (fp32 summation order apart)
+    xrank = None
+    if world > 1:
+        def digest(t):
+            b = t.detach().contiguous().view(torch.int32).to(torch.int64)
+            return (b * (torch.arange(b.numel(), device=b.device) % 1000003 + 1)).sum().reshape(1)
+        mine = torch.cat([digest(h.prototypes), digest(h.squared_mean)])
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        identical = all(torch.equal(a, allh[0]) for a in allh)
+        # two more steps from a common state, sharded, vs rank 0 alone on the gathered batch
+        start = [t.clone() for t in (h.prototypes, h.squared_mean, h.counter)]
+        for i in range(2):
+            eager_step(i)
+        torch.cuda.synchronize()
+        gathered = []
+        for i in range(2):
+            parts = []
+            for x in sets[i]:
+                buf = [torch.empty_like(x) for _ in range(world)]
+                dist.all_gather(buf, x)
+                parts.append(torch.cat(buf))
+            gathered.append(parts)
+        relerr = None
+        if rank == 0:
+            h1 = prototype_handler(impl=args.kernel, **PARAMS)
+            h1.prototypes, h1.squared_mean, h1.counter = (t.clone() for t in start)
+            for i in range(2):
+                feat, prior, out = gathered[i]
+                h1.pseudo_labels_fused(feat, prior, out)
+                h1.ma(feat, out)
+            relerr = max(float((h1.prototypes - h.prototypes).abs().max() / h.prototypes.abs().max()),
+                         float((h1.squared_mean - h.squared_mean).abs().max() / h.squared_mean.abs().max()))
+        del gathered
+        xrank = {"xrank_identical": bool(identical), "vs_single_gpu_relerr": relerr}
+        barrier()
+
+    host = [tuple(x.cpu().pin_memory() for x in s) for s in sets[:2]]
+    dev_in = [tuple(torch.empty_like(x) for x in s) for s in sets[:2]]
     lab_host = torch.empty((N, 1), dtype=torch.int64).pin_memory()
+    soft_host = torch.empty((N, C), dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device)
     mon = Monitor(200, 0.003, "hamming")
     h2d_bytes = sum(x.numel() * x.element_size() for x in host[0])
-    d2h_bytes = lab_host.numel() * 8 + nat.NUM_STATS * 4
+    d2h_bytes = lab_host.numel() * 8 + soft_host.numel() * 4 + nat.NUM_STATS * 4
 
     def upload(i, after=None):
         with torch.cuda.stream(copy_stream):
@@ -310,6 +431,7 @@ def run_onda(args):
             labels, soft = h.pseudo_labels_fused(feat, prior, out, confidence_monitor=mon)   # reads the stats (D2H)
             h.ma(feat, out)
             lab_host.copy_(labels, non_blocking=True)
+            soft_host.copy_(soft, non_blocking=True)
             prev_done = torch.cuda.Event()
             prev_done.record()
         torch.cuda.synchronize()
@@ -336,29 +458,36 @@ def run_onda(args):
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "host_enqueue_ms_per_step": host_ms, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": ms / args.steps, "host_enqueue_ms_per_step": host_ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(d, world, args.allreduce),
-                       launch="CUDA graph replay (one graph per input set)" if graphs is not None else "eager launches"),
+        "config": workload_config(d, world, args),
+        "launch_mode": "CUDA graph replay (one graph per input set)" if graphs is not None else "eager launches",
+        "input_sets": len(sets),
+        "exchange": (None if world == 1 else
+                     {"requested": args.allreduce, "effective": h.allreduce,
+                      "peer_memory": bool(h._symm is not None), "fused_into_ema_kernel": bool(h._symm is not None and h.allreduce == "oneshot")}),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(d) if args.kernel in ("auto", "tcgen05") else None,
-                     "traffic_source": "profiles/r1_tc_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "traffic_source": "profiles/r2_tc_traffic.json (ncu --set full capture of this command, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                      "kernel": f"fused pseudo-label pass ({h.impl})", "kernel_ms": kernel_ms,
                      "launches_timed": int(n_timed.value), "bytes_per_px": algorithmic_bytes_per_pixel(d),
                      "peak_source": peak_src, "step_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
     }
+    if xrank is not None:
+        line.update(xrank)
     if world == 1:
         threads = os.cpu_count() or 1
-        images = 4 if d <= 256 else 1
-        px, times = cpu_reference_rate(torch, d, images, 3, 1, threads)
+        reps = 3 if d <= 256 else 1
+        px, times, kind = cpu_reference_rate(torch, d, B_PER_GPU, reps, 1, threads)
         best = min(times)
-        line["cpu_baseline"] = {"value": px / best, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{images} of {B_PER_GPU} images ({px} px), best of 3 after 1 warm-up, "
-                                          "oracle port of the reference torch path"}
+        what = "the reference's prototype_handler (oracle/_ref)" if kind == "reference" else "oracle port of the reference torch path"
+        line["cpu_baseline"] = {"value": px / best, "unit": UNIT, "cores": threads, "kind": kind,
+                                "sample": f"the full batch ({B_PER_GPU} images, {px} px), best of {reps} after 1 warm-up, {what}"}
+        line["aux_kernels"] = aux_kernel_numbers(torch, device)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -375,7 +504,9 @@ def main():
                     help="exchange of the class-sum buffer at N>1: NCCL all_reduce or the library's one-shot NVLink kernel")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="time eager launches instead of CUDA-graph replays (single-GPU runs replay graphs by default)")
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU (default 32 = the bench workload)")
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU (weak) or in total (strong); default 32 = the bench workload")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch images on every GPU; strong: --batch images in total, split over the GPUs")
     ap.add_argument("--label-block", type=int, default=8, help="side of the constant-label blocks of the synthetic maps")
     ap.add_argument("--logit-margin", type=float, default=4.0, help="logit bonus of the block's label (coherence of the argmax)")
     ap.add_argument("--d", type=int, default=256, help="feature width (256 = real ProDA head, 2048 = stress size)")
