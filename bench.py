@@ -368,7 +368,7 @@ def run_onda(args):
     xrank = None
     if world > 1:
         def digest(t):
-            b = t.detach().contiguous().view(torch.int32).to(torch.int64)
+            b = t.detach().contiguous().reshape(-1).view(torch.int32).to(torch.int64)
             return (b * (torch.arange(b.numel(), device=b.device) % 1000003 + 1)).sum().reshape(1)
         mine = torch.cat([digest(h.prototypes), digest(h.squared_mean)])
         allh = [torch.empty_like(mine) for _ in range(world)]

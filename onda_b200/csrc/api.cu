@@ -24,6 +24,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 static unsigned long long g_launches = 0;
+static long long* g_debug = nullptr;       // optional device buffer for cycle / time stamps (onda_debug_set_buffer)
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 // ---- optional kernel timing (roofline report) ----------------------------------------------
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
                                                               float* __restrict__ table, const float* __restrict__ sums,
                                                               float lam, PeerTable peers, int rank, int world,
                                                               uint32_t epoch, float* __restrict__ sums_out,
-                                                              uint32_t* __restrict__ epoch_counter) {
+                                                              uint32_t* __restrict__ epoch_counter,
+                                                              long long* __restrict__ stamps) {
     // world > 0: `sums` of every rank sit in peer-mapped slots; this kernel is also the all-reduce -- handshake,
     // then every use of sums[i] is the rank-ordered sum over the peers (identical on every rank), and the reduced
     // buffer is written to sums_out for the statistics readers.
@@ -96,8 +98,18 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
     __shared__ float cn[32];               // pixel count of every class (the EMA's cnt_k)
     // the epoch of this exchange: a host argument, or (graph replay: arguments are frozen) a device counter that the
     // last CTA of this grid bumps for the next call
+    // optional time stamps of CTA 0 (exchange breakdown, profiles/exchange_probe.py): start | handshake done | gather done | end
+    auto stamp = [&](int i) {
+        if (stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+            long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            stamps[i] = t;
+        }
+    };
+    stamp(0);
     if (gather && epoch_counter != nullptr) epoch = *reinterpret_cast<volatile uint32_t*>(epoch_counter);
     if (gather) peer_handshake(peers, rank, world, epoch);
+    stamp(1);
     __shared__ float gs[2 * 32 * 32];      // gather: the reduced (sum | sum of squares)[class][this CTA's 32 channels]
     if (gather) {
         // all threads fetch the CTA's slice of every rank's sums with independent (16-byte when possible) loads:
@@ -145,6 +157,8 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
             if (gather && blockIdx.x == 0) sums_out[tail0 + threadIdx.x] = v;
         }
     }
+    if (gather) __syncthreads();
+    stamp(2);
     __shared__ double wk[32];              // c_k / sum_k c_k
     __shared__ double mom[4][3][32];       // per warp: partial (gm, gsq, mean) of each channel
     __shared__ double bpart[4][32];        // per warp: partial bias of its classes
@@ -256,6 +270,7 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
         }
     }
     if (last_flag && gather) peer_publish_done(peers, rank, world, epoch);          // every CTA's peer reads are complete
+    stamp(3);
 }
 
 __global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
@@ -673,7 +688,6 @@ int onda_sm_count(void) {
 
 unsigned long long onda_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
-static long long* g_debug = nullptr;
 int onda_debug_set_buffer(void* device_buffer) {
     g_debug = (long long*)device_buffer;
     return ONDA_OK;
@@ -721,7 +735,12 @@ static Workspace fused_workspace(int B, int D, int HW, int C) {
     w.off_cta = 0;
     w.off_stat = align256(w.off_cta + (size_t)w.max_cta * sums_floats(C, D) * sizeof(float));
     w.off_dots = align256(w.off_stat + (size_t)w.max_stat * kStatSlots * sizeof(float));
-    const size_t dots = pl.nslices > 1 ? (size_t)pl.nslices * (padded_classes(C) + 1) * (size_t)B * HW * sizeof(float) : 0;
+    int slices = pl.nslices;
+    if (tc_supported(B, D, HW, C)) {
+        const int ts = tc_slices(tc_tiles(B, HW), D, sms);
+        slices = ts > slices ? ts : slices;
+    }
+    const size_t dots = slices > 1 ? (size_t)slices * (padded_classes(C) + 1) * (size_t)B * HW * sizeof(float) : 0;
     w.total = align256(w.off_dots + dots);
     return w;
 }
@@ -747,7 +766,7 @@ int onda_build_distance_table(const float* prototypes, const float* squared_mean
     if (metric == ONDA_METRIC_MAHALANOBIS)
         ONDA_REQUIRE(squared_mean && counter, "onda_build_distance_table: mahalanobis needs squared_mean and counter");
     table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(const_cast<float*>(prototypes), const_cast<float*>(squared_mean), counter, C, D, metric,
-                                                                                   table, nullptr, 0.f, PeerTable{}, 0, 0, 0u, nullptr, nullptr);
+                                                                                   table, nullptr, 0.f, PeerTable{}, 0, 0, 0u, nullptr, nullptr, nullptr);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
@@ -800,7 +819,7 @@ int onda_pseudolabel_fused_guarded(const float* feat, const float* prior, const 
     const long long n_tiles = ((long long)B * HW + kTilePixels - 1) / kTilePixels;
     const bool tc_ok = want_dist && tc_supported(B, D, HW, C);
     ONDA_REQUIRE(impl != ONDA_IMPL_TCGEN05 || tc_ok || !want_dist,
-                 "onda_pseudolabel_fused: the tcgen05 kernel covers D = 64, 128, 192 or 256 and C <= 32 "
+                 "onda_pseudolabel_fused: the tcgen05 kernel covers D % 64 == 0 and C <= 32 "
                  "(got D=%d C=%d)", D, C);
     // AUTO: tensor-core kernel when the shape allows and there are enough tiles to fill the machine
     const bool use_tc = tc_ok && (impl == ONDA_IMPL_TCGEN05 || (impl == ONDA_IMPL_AUTO && n_tiles >= 32));
@@ -825,13 +844,20 @@ int onda_pseudolabel_fused_guarded(const float* feat, const float* prior, const 
 
     int n_cta, n_stat;
     if (use_tc) {
-        p.nslices = 1; p.slice_channels = D; p.cluster = 1;
         p.tiles_per_img = (HW + kTilePixels - 1) / kTilePixels;
         p.tiles = tc_tiles(B, HW);
-        n_cta = tc_grid(p.tiles, sms);
+        const int slices = tc_slices(p.tiles, D, sms);
+        p.nslices = slices; p.slice_channels = D / slices; p.cluster = 1;
+        n_cta = tc_grid(p.tiles, sms, slices);
         n_stat = n_cta;
         int rc = launch_fused_tc(p, n_cta, want_sums, stream);
         if (rc != ONDA_OK) return rc;
+        if (slices > 1) {          // the per-pixel tail over the parked partial dot products
+            FusedParams f = p;
+            f.tiles = pl.tiles;    // tiles of the flattened pixel axis
+            rc = launch_split_finish(f, sms, &n_stat, stream);
+            if (rc != ONDA_OK) return rc;
+        }
     } else {
         int rc = launch_fused_simt(p, pl, want_dist, want_sums, stream);
         if (rc != ONDA_OK) return rc;
@@ -866,7 +892,7 @@ int onda_ema_update_and_table(float* prototypes, float* squared_mean, const floa
                  "onda_ema_update_and_table: unexpected value for attribute distance_metric (%d)", metric);
     if (metric == ONDA_METRIC_MAHALANOBIS) ONDA_REQUIRE(counter, "onda_ema_update_and_table: mahalanobis needs counter");
     table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
-                                                                                   table, sums, ma_lambda, PeerTable{}, 0, 0, 0u, nullptr, nullptr);
+                                                                                   table, sums, ma_lambda, PeerTable{}, 0, 0, 0u, nullptr, nullptr, g_debug);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
@@ -889,7 +915,7 @@ int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, 
         ONDA_REQUIRE(peer_bufs_host[r] && peer_flags_host[r], "onda_ema_update_and_table_allreduce: null peer pointer for rank %d", r);
     const PeerTable peers = make_peer_table(rank, world, peer_bufs_host, peer_flags_host, peer_done_host);
     table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
-                                                                                   table, nullptr, ma_lambda, peers, rank, world, epoch, sums_out, epoch_counter);
+                                                                                   table, nullptr, ma_lambda, peers, rank, world, epoch, sums_out, epoch_counter, g_debug);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;

@@ -41,8 +41,12 @@ int launch_fused_simt(const FusedParams& p, const SimtPlan& pl, bool dist, bool 
 // tcgen05 kernel (fused_tc.cu)
 bool tc_supported(int B, int D, int HW, int C);
 int tc_tiles(int B, int HW);
-int tc_grid(int tiles, int sms);
+int tc_slices(int tiles, int D, int sms);
+int tc_grid(int tiles, int sms, int slices);
 int launch_fused_tc(const FusedParams& p, int grid, bool sums, cudaStream_t stream);
+// completes pixels whose dot products were parked per channel slice (fused_simt.cu); returns the number of CTAs that
+// wrote statistics partials
+int launch_split_finish(const FusedParams& p, int sms, int* n_stat, cudaStream_t stream);
 
 struct PixelStats {
     float proto_conf = 0.f, prior_conf = 0.f, pl_conf = 0.f, entropy = 0.f;

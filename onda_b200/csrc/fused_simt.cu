@@ -366,6 +366,19 @@ static int launch_one(const FusedParams& p, const SimtPlan& pl, cudaStream_t str
     return ONDA_OK;
 }
 
+int launch_split_finish(const FusedParams& p, int sms, int* n_stat, cudaStream_t stream) {
+    int grid = p.tiles < 4 * sms ? p.tiles : 4 * sms;
+    if (grid < 1) grid = 1;
+    const int CP = padded_classes(p.C);
+    const size_t sm = (size_t)(kTilePixels * (CP + 1) + 4 * kStatSlots) * sizeof(float);
+    if (CP == 20) split_finish_kernel<20><<<grid, kSimtThreads, sm, stream>>>(p);
+    else split_finish_kernel<32><<<grid, kSimtThreads, sm, stream>>>(p);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    *n_stat = grid;
+    return ONDA_OK;
+}
+
 int launch_fused_simt(const FusedParams& p, const SimtPlan& pl, bool dist, bool sums, cudaStream_t stream) {
     const int CP = padded_classes(p.C);
 #define ONDA_DISPATCH(CPV)                                                         \

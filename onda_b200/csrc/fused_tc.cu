@@ -1,4 +1,5 @@
-// tcgen05 implementation of the fused pass for sm_100a (64 <= D <= 256, D % 64 == 0, C <= 32).
+// tcgen05 implementation of the fused pass for sm_100a (D % 64 == 0, C <= 32; widths above 256 and small batches run as
+// channel slices of at most 256 channels per CTA whose partial dot products split_finish_kernel adds up).
 //
 // Why tensor cores: the CUDA-core kernel (fused_simt.cu) is issue-bound -- 21 FFMA per feature
 // element for the 19-wide contraction alone (profiles/r1_simt_v1_ncu_full.txt) -- so the distance
@@ -294,7 +295,7 @@ struct TcMaps {
     int shift[4];
 };
 
-template <int CP, int CE, bool SUMS, bool WANT_DIST, bool PROF>
+template <int CP, int CE, bool SUMS, bool WANT_DIST, bool PROF, bool PARTIAL>
 __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedParams p, const __grid_constant__ TcMaps maps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const long long t_entry = PROF ? clock64() : 0;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     const int Dc = p.slice_channels;      // channels this CTA contracts over
     const int NB = Dc / kTcChunkC;        // even (tc_supported)
     const int nstage = p.nstage;
-    const int c_base = 0;                 // first channel of this CTA's slice
+    const int c_base = (int)blockIdx.y * Dc;     // first channel of this CTA's slice (gridDim.y slices of Dc channels; PARTIAL when > 1)
     const TcSmem L = tc_smem(Dc, C, CP, SUMS, nstage);
     float* Btab = reinterpret_cast<float*>(smem_raw + L.btab);
     float* acc = reinterpret_cast<float*>(smem_raw + L.acc);
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const long long n0 = (long long)img * HW + pix0;
             float pri[CP];
             {   // prior row of this pixel: issued before the wait so its latency hides behind the MMAs
-                if (et < npx && p.prior != nullptr && (p.labels != nullptr || p.soft != nullptr)) {
+                if (!PARTIAL && et < npx && p.prior != nullptr && (p.labels != nullptr || p.soft != nullptr)) {
                     load_pixel_row_at<CP>(p.prior + ((size_t)img * C) * HW + pix0 + et, C, HWu, pri);
                 } else {
 #pragma unroll
@@ -645,12 +646,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             for (int b = 0; b < 8; ++b) a_tot += b < NB ? __uint_as_float(av[b]) : 0.f;
             tc_fence_before();
             mbar_arrive(acc_empty(par));
+            if (PARTIAL) {
+                // this CTA covers one channel slice: park the partial dot products (scaled back by -1/2: B holds -2 Q)
+                // and the partial sum_j w_j x'_j^2 for split_finish_kernel, which adds the slices in order
+                if (et < npx) {
+                    float* dst = p.dots_scratch + ((size_t)blockIdx.y * (CP + 1)) * p.N + (n0 + et);
 #pragma unroll
-            for (int k = 0; k < CP; ++k) d2[k] = (a_tot + __ldg(bias + k)) + (d2[k] + __uint_as_float(dv[k]));
-            finish_pixel_rows<CP, WANT_DIST>(p, C, d2, n0, npx, et, out_stage, st, pri);
+                    for (int k = 0; k < CP; ++k) dst[(size_t)k * p.N] = -0.5f * (d2[k] + __uint_as_float(dv[k]));
+                    dst[(size_t)CP * p.N] = a_tot;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < CP; ++k) d2[k] = (a_tot + __ldg(bias + k)) + (d2[k] + __uint_as_float(dv[k]));
+                finish_pixel_rows<CP, WANT_DIST>(p, C, d2, n0, npx, et, out_stage, st, pri);
+            }
         }
         // fixed-order reduction of the statistics over the four epilogue warps
-        {
+        if (!PARTIAL) {
             float v[kStatSlots] = {st.proto_conf, st.prior_conf, st.pl_conf, (float)st.pl_pixels, (float)st.pixels,
                                    st.entropy, 0.f, 0.f};
             const int ew = et >> 5;
@@ -846,7 +858,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const int stat = i >= cd, rem = i - stat * cd, k = rem / Dc, j = rem - k * Dc;
             out[(size_t)(stat * C + k) * D + c_base + j] = acc[((k * NB + (j >> 5)) * 2 + stat) * 32 + (j & 31)];
         }
-        if (tid < C) out[(size_t)2 * C * D + tid] = (float)cnt[tid];
+        if (tid < C && blockIdx.y == 0) out[(size_t)2 * C * D + tid] = (float)cnt[tid];
     }
     if (warp == kTcMmaWarp) {
         tc_fence_after();
@@ -863,14 +875,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
+// channels per CTA: the whole width up to 256, else the largest of 256 / 192 / 128 / 64 that divides D (a tile is then
+// split over D / slice CTAs whose partial dot products meet in split_finish_kernel)
+int tc_slice_channels(int D) {
+    if (D % 64 != 0 || D < 64) return 0;
+    if (D <= 256) return D;
+    for (int dc = 256; dc >= 64; dc -= 64)
+        if (D % dc == 0) return dc;
+    return 0;
+}
+
 bool tc_supported(int B, int D, int HW, int C) {
-    if (!(D % 64 == 0 && D >= 64 && D <= 256 && C >= 1 && C <= 32)) return false;
-    return tc_ring_stages(D, C, padded_classes(C), true) >= 3;
+    (void)B; (void)HW;
+    const int dc = tc_slice_channels(D);
+    if (dc == 0 || D / dc > 16 || C < 1 || C > 32) return false;
+    return tc_ring_stages(dc, C, padded_classes(C), true) >= 3;
 }
 
 int tc_tiles(int B, int HW) { return B * ((HW + kTilePixels - 1) / kTilePixels); }
 
-int tc_grid(int tiles, int sms) { return tiles < sms ? tiles : sms; }
+// Channel slices of a launch: D / tc_slice_channels(D) when the width needs it; with few tiles (small batches) the
+// width is halved once more so that more SMs have work.
+int tc_slices(int tiles, int D, int sms) {
+    int dc = tc_slice_channels(D);
+    if (tiles * (D / dc) * 2 <= sms && dc % 128 == 0) dc /= 2;
+    return D / dc;
+}
+
+int tc_grid(int tiles, int sms, int slices) {
+    const int per_slice = sms / slices > 0 ? sms / slices : 1;
+    return tiles < per_slice ? tiles : per_slice;
+}
 
 // ---- tensor maps of the feature map (see the header): built with the driver's cuTensorMapEncodeTiled, fetched through
 // the runtime so the library does not link libcuda; the last few encodings are kept (a training step alternates
@@ -922,9 +957,9 @@ static int tc_make_maps(const float* feat, int B, int D, int HW, TcMaps* out) {
     return ONDA_OK;
 }
 
-template <int CP, int CE, bool SUMS, bool WANT_DIST, bool PROF>
+template <int CP, int CE, bool SUMS, bool WANT_DIST, bool PROF, bool PARTIAL>
 static int launch_tc(FusedParams p, int grid, cudaStream_t stream) {
-    auto kern = fused_tc_kernel<CP, CE, SUMS, WANT_DIST, PROF>;
+    auto kern = fused_tc_kernel<CP, CE, SUMS, WANT_DIST, PROF, PARTIAL>;
     p.nstage = tc_ring_stages(p.slice_channels, p.C, CP, SUMS);
     const size_t smem = tc_smem(p.slice_channels, p.C, CP, SUMS, p.nstage).total;
     static size_t smem_set[kMaxDevices] = {};     // per instantiation and device: raise the attribute only when a launch needs more
@@ -937,7 +972,7 @@ static int launch_tc(FusedParams p, int grid, cudaStream_t stream) {
     const int rc = tc_make_maps(p.feat, p.B, p.D, p.HW, &maps);
     if (rc != ONDA_OK) return rc;
     timing_begin(stream);
-    kern<<<grid, kTcThreads, smem, stream>>>(p, maps);
+    kern<<<dim3((unsigned)grid, (unsigned)(p.D / p.slice_channels)), kTcThreads, smem, stream>>>(p, maps);
     timing_end(stream);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
@@ -947,9 +982,11 @@ static int launch_tc(FusedParams p, int grid, cudaStream_t stream) {
 template <int CP, int CE>
 static int launch_tc_cp(const FusedParams& p, int grid, bool sums, cudaStream_t stream) {
     const bool dist = p.dist != nullptr;
-    if (p.debug != nullptr && sums && !dist) return launch_tc<CP, CE, true, false, true>(p, grid, stream);   // diagnostics build
-    if (sums) return dist ? launch_tc<CP, CE, true, true, false>(p, grid, stream) : launch_tc<CP, CE, true, false, false>(p, grid, stream);
-    return dist ? launch_tc<CP, CE, false, true, false>(p, grid, stream) : launch_tc<CP, CE, false, false, false>(p, grid, stream);
+    if (p.slice_channels < p.D)       // channel slices: the per-pixel tail runs in split_finish_kernel
+        return sums ? launch_tc<CP, CE, true, false, false, true>(p, grid, stream) : launch_tc<CP, CE, false, false, false, true>(p, grid, stream);
+    if (p.debug != nullptr && sums && !dist) return launch_tc<CP, CE, true, false, true, false>(p, grid, stream);   // diagnostics build
+    if (sums) return dist ? launch_tc<CP, CE, true, true, false, false>(p, grid, stream) : launch_tc<CP, CE, true, false, false, false>(p, grid, stream);
+    return dist ? launch_tc<CP, CE, false, true, false, false>(p, grid, stream) : launch_tc<CP, CE, false, false, false, false>(p, grid, stream);
 }
 
 int launch_fused_tc(const FusedParams& p, int grid, bool sums, cudaStream_t stream) {
