@@ -509,7 +509,7 @@ def main():
                     help="weak: --batch images on every GPU; strong: --batch images in total, split over the GPUs")
     ap.add_argument("--label-block", type=int, default=8, help="side of the constant-label blocks of the synthetic maps")
     ap.add_argument("--logit-margin", type=float, default=4.0, help="logit bonus of the block's label (coherence of the argmax)")
-    ap.add_argument("--d", type=int, default=256, help="feature width (256 = real ProDA head, 2048 = stress size)")
+    ap.add_argument("--d", "--dim", dest="d", type=int, default=256, help="feature width (256 = real ProDA head, 2048 = stress size; --dim is the spelling to use under torchrun, whose own parser claims --d)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     globals()["B_PER_GPU"] = args.batch

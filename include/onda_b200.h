@@ -139,6 +139,16 @@ int onda_pseudolabel_fused_guarded(const float* feat, const float* prior, const 
                                    const uint32_t* peer_done, const uint32_t* peer_epoch, int peer_world, void* stream);
 
 /* ---- prototype updates ------------------------------------------------------ */
+/*
+ * Class sums keyed by labels given directly, straight from the NCHW feature map: sums = { sum_{n: id_n = k} x_n,
+ * sum of squares, count } for class_ids[N] (int64; values outside [0, C), e.g. the ignore label 255, are skipped;
+ * the statistics tail is zero).  Replaces the mask-gather + transposition + one-hot matmul of
+ * online_proDA.calculate_prototypes with STARTING_PROTO == "source"
+ * (framework/domain_adaptation/methods/prototypes.py:142-154) in front of append().
+ */
+int onda_class_sums_labelled(const float* feat, const int64_t* class_ids, int B, int D, int HW, int C, float* sums,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ma(): P_k <- P_k*rho_k + (1-rho_k)*sum_k/max(cnt_k,1), rho_k = lambda if cnt_k>0 else 1; same for the
  * squared mean; counter untouched.  prototype_handler.py:88-99. */
 int onda_ema_update(float* prototypes, float* squared_mean, const float* sums, int C, int D, float ma_lambda,

@@ -41,6 +41,7 @@ _SIGNATURES = {
                                          _p, _p, _p, _p, _p, C.c_size_t, C.c_int, _p]),
     "onda_pseudolabel_fused_guarded": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                                  _p, _p, _p, _p, _p, C.c_size_t, C.c_int, _p, _p, C.c_int, _p]),
+    "onda_class_sums_labelled": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, C.c_size_t, _p]),
     "onda_ema_update": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_float, _p]),
     "onda_ema_update_and_table": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_float, C.c_int, _p, _p]),
     "onda_append_update": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, _p]),

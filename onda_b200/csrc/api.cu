@@ -874,6 +874,36 @@ int onda_pseudolabel_fused_guarded(const float* feat, const float* prior, const 
     return ONDA_OK;
 }
 
+int onda_class_sums_labelled(const float* feat, const int64_t* class_ids, int B, int D, int HW, int C, float* sums,
+                             void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ONDA_REQUIRE(feat && class_ids && sums && workspace, "onda_class_sums_labelled: null pointer");
+    ONDA_REQUIRE(B > 0 && D > 0 && HW > 0 && C > 0 && C <= ONDA_MAX_CLASSES, "onda_class_sums_labelled: bad shape");
+    const Workspace ws = fused_workspace(B, D, HW, C);
+    ONDA_REQUIRE(workspace_bytes >= ws.total, "onda_class_sums_labelled: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    const int sms = cached_sm_count();
+    const SimtPlan pl = plan_simt(B, D, HW, C, sms, false, true);
+    FusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.feat = feat; p.class_ids = (const long long*)class_ids;
+    p.B = B; p.D = D; p.HW = HW; p.C = C; p.N = (long long)B * HW;
+    p.tau = 1.f; p.inv_tau = 1.f;
+    char* base = (char*)workspace;
+    p.cta_partials = (float*)(base + ws.off_cta);
+    p.stat_partials = (float*)(base + ws.off_stat);
+    p.dots_scratch = (float*)(base + ws.off_dots);
+    p.nslices = pl.nslices; p.slice_channels = pl.DS; p.tiles = pl.tiles;
+    int rc = launch_fused_simt(p, pl, false, true, stream);
+    if (rc != ONDA_OK) return rc;
+    const int class_elems = 2 * C * D + C;
+    reduce_partials_kernel<<<(class_elems + kStatSlots + 31) / 32, 256, 0, stream>>>(p.cta_partials, pl.grid_x, sums_floats(C, D),
+                                                                                   class_elems, 1, p.stat_partials, 0, 0, sums,
+                                                                                   nullptr, nullptr, 0);
+    ONDA_CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    return ONDA_OK;
+}
+
 int onda_ema_update(float* prototypes, float* squared_mean, const float* sums, int C, int D, float ma_lambda,
                     void* stream) {
     ONDA_REQUIRE(prototypes && squared_mean && sums && C > 0 && D > 0, "onda_ema_update: bad argument");

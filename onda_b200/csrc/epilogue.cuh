@@ -10,7 +10,8 @@ namespace onda {
 struct FusedParams {
     const float* feat;     // (B, D, HW)
     const float* prior;    // (B, C, HW) or null
-    const float* logits;   // (B, C, HW) or null -> no class sums
+    const float* logits;   // (B, C, HW) or null -> no class sums (unless class_ids is given)
+    const long long* class_ids;   // [N] or null: the class of every pixel given directly (values outside [0, C) are skipped)
     const float* table;    // distance table (common.cuh: TableLayout)
     int B, D, HW, C;
     long long N;           // B * HW

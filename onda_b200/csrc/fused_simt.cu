@@ -89,9 +89,14 @@ __global__ void __launch_bounds__(kSimtThreads, 2) fused_simt_kernel(const Fused
             const long long n = tile_base + tid;
             int arg = -1;
             if (n < p.N) {
-                float lv[CP];
-                load_pixel_row<CP>(p.logits, C, HW, n, lv);
-                arg = first_argmax<CP>(lv, C);
+                if (p.class_ids != nullptr) {        // source labels (calculate_prototypes): 255 / out-of-range = not counted
+                    const long long id = p.class_ids[n];
+                    arg = (id >= 0 && id < C) ? (int)id : -1;
+                } else {
+                    float lv[CP];
+                    load_pixel_row<CP>(p.logits, C, HW, n, lv);
+                    arg = first_argmax<CP>(lv, C);
+                }
             }
             ys[tid] = arg;
         }

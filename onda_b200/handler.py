@@ -620,9 +620,42 @@ class prototype_handler:
         self._epoch += 1
         self._table = {metric: (self._table_key(P, S, cnt, need_stats, device), table)}
 
+    def append_source_labels(self, feat, labels, num_classes=None):
+        """``calculate_prototypes`` with ``STARTING_PROTO == "source"`` in one pass (prototypes.py:142-154): ``labels``
+        (B, H, W) ground truth at any resolution is nearest-resized to the feature map like the reference does
+        (``F.interpolate(labels.unsqueeze(1).float(), size=(h, w))``), pixels labelled 255 (or anything outside
+        ``[0, num_classes)``) are skipped, and the class sums are taken straight from the NCHW ``feat`` -- no mask-gather,
+        no transposition copy, no one-hot matrix -- before the cumulative ``append`` update (:62-74)."""
+        self._require_cuda(feat, "feat")
+        if feat.dim() != 4:
+            raise ValueError(f"feat must be (B, D, h, w), got {tuple(feat.shape)}")
+        B, D, h, w = feat.shape
+        C = num_classes if num_classes is not None else self._num_classes()
+        if C is None:
+            raise ValueError("num_classes is needed before the prototypes exist")
+        if C > nat.MAX_CLASSES:
+            raise ValueError(f"{C} classes unsupported (max {nat.MAX_CLASSES})")
+        labels = torch.as_tensor(labels)
+        if labels.dim() != 3 or labels.shape[0] != B:
+            raise ValueError(f"labels must be (B, H, W) with B={B}, got {tuple(labels.shape)}")
+        device = feat.device
+        ids = torch.nn.functional.interpolate(labels.to(device).unsqueeze(1).float(), size=(h, w)).view(-1).to(torch.int64)
+        feat3 = self._nchw(feat, "feat")
+        n = self._lib.onda_sums_floats(C, D)
+        sums = torch.empty((n,), dtype=torch.float32, device=device)
+        with _on(device):
+            wbytes = self._lib.onda_fused_workspace_bytes(B, D, h * w, C, nat.IMPL["simt"])
+            work = self._buf("work", (wbytes,), torch.uint8, device)
+            nat.check(self._lib.onda_class_sums_labelled(nat.ptr(feat3), nat.ptr(ids), B, D, h * w, C, nat.ptr(sums),
+                                                         nat.ptr(work), wbytes, _stream_ptr(device)), "onda_class_sums_labelled")
+        self._append_sums(sums, D, C, device)
+
     def append(self, feat, out):
         """Cumulative-mean update used to initialise the prototypes (:62-74)."""
         sums, D, C, device = self._class_sums(feat, out)
+        self._append_sums(sums, D, C, device)
+
+    def _append_sums(self, sums, D, C, device):
         sums = self._allreduce(sums)
         if isinstance(self.prototypes, int):     # first call allocates the state (:68-70)
             self.prototypes = torch.zeros((C, D), dtype=torch.float32, device=device)
