@@ -44,7 +44,7 @@ extern "C" {
 /* kernel selection for onda_pseudolabel_fused (ONDA_IMPL_AUTO picks tcgen05 when the shape allows) */
 #define ONDA_IMPL_AUTO 0
 #define ONDA_IMPL_SIMT 1    /* CUDA-core kernel, any shape */
-#define ONDA_IMPL_TCGEN05 2 /* 3xTF32 tcgen05.mma kernel: D = 128 or 256, C <= 32 (see onda_impl_supported) */
+#define ONDA_IMPL_TCGEN05 2 /* 3xTF32 tcgen05.mma kernel: D % 64 == 0, C <= 32 (see onda_impl_supported) */
 
 /* Number of statistic slots at the tail of a `sums` buffer (see onda_sums_floats). */
 #define ONDA_NUM_STATS 8
@@ -185,6 +185,25 @@ size_t onda_step_log_workspace_bytes(void);
 int onda_step_log_stats(const int64_t* labels, const float* student_logits, const float* prototypes, int B, int C, int HW,
                         int D, float* out4, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Loss-side consumers of the pseudo-labels, forward + gradient in one pass over the student logits [B, C, HW]
+ * (online_proDA.pseudolabel_loss, prototypes.py:313-336, hard labels):
+ *   out6[0] = ce    = cross_entropy_2d(logits, labels)          framework/utils/loss.py:16-45
+ *   out6[1] = rce   = rce(logits, labels)                        framework/utils/loss.py:88-112
+ *   out6[2] = reg   = regular_loss(regularizer, logits)          prototypes.py:29-39 (ONDA_REG_*)
+ *   out6[3] = alpha * ce + beta * rce + reg_weight * reg         (RCE_ALPHA, RCE_BETA, REGULARIZER_WEIGHT)
+ *   out6[4] = mean(labels == argmax_k logits)                    "output & prototype agreement", prototypes.py:346-347
+ *   out6[5] = number of labels that are neither negative nor 255
+ *   grad[B, C, HW] (may be NULL) = d out6[3] / d logits.
+ * `labels` [B*HW] int64 in the pixel order of the fused pass, 255 = ignore.  `n_valid` (device, may be NULL): that
+ * count as a float, e.g. &sums[2*C*D + C + ONDA_STAT_PL_PIXELS] of the fused pass; NULL adds a counting launch.
+ * `workspace`: onda_target_loss_workspace_bytes() bytes, zero-filled before its first use.
+ */
+size_t onda_target_loss_workspace_bytes(void);
+int onda_target_loss_fused(const float* student_logits, const int64_t* labels, int B, int C, int HW, const float* n_valid,
+                           float alpha, float beta, float reg_weight, int regularizer, float* grad, float* out6,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- model-weight EMA ("next" row f2 of the scope table) --------------------------------------------------
  * update_ema (framework/domain_adaptation/methods/prototypes.py:407-416) walks every parameter in a Python loop with
  * two clones and three kernels each, then copies every buffer.  Here: ONE launch over a table of chunks that the
@@ -192,6 +211,10 @@ int onda_step_log_stats(const int64_t* labels, const float* student_logits, cons
  * rounded, then the sum: bit-identical to `param_k.clone()*a + param_q.clone()*(1-a)` with keep = (float)a,
  * take = (float)(1.0 - a)); mode 1: copy `count` bytes (buffers of any dtype, ":414-416").  A chunk is at most
  * ONDA_EMA_CHUNK_BYTES long. */
+#define ONDA_REG_NONE 0
+#define ONDA_REG_MRKLD 1 /* regular_loss, framework/domain_adaptation/methods/prototypes.py:36-39 */
+#define ONDA_REG_MRENT 2 /* :32-35 */
+
 #define ONDA_EMA_CHUNK_BYTES 32768
 typedef struct {
     const void* src; /* the trained model's tensor (chunk start) */

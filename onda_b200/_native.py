@@ -16,6 +16,7 @@ IMPL = {"auto": 0, "simt": 1, "tcgen05": 2}
 NUM_STATS = 8
 STAT_PROTO_CONF, STAT_PRIOR_CONF, STAT_PL_CONF, STAT_PL_PIXELS, STAT_PIXELS, STAT_ENTROPY = range(6)
 IGNORE_LABEL = 255
+REGULARIZER = {None: 0, "": 0, "MRKLD": 1, "MRENT": 2}
 MAX_CLASSES = 32
 
 _lib = None
@@ -50,6 +51,9 @@ _SIGNATURES = {
     "onda_prior_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "onda_step_log_workspace_bytes": (C.c_size_t, []),
     "onda_step_log_stats": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, C.c_size_t, _p]),
+    "onda_target_loss_workspace_bytes": (C.c_size_t, []),
+    "onda_target_loss_fused": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, C.c_float, C.c_float, C.c_float, C.c_int,
+                                         _p, _p, _p, C.c_size_t, _p]),
     "onda_weight_ema_update": (C.c_int, [_p, C.c_int, C.c_float, C.c_float, _p]),
     "onda_confusion_update": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p]),
     "onda_allreduce_oneshot": (C.c_int, [_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(_p), C.POINTER(_p),

@@ -14,7 +14,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libonda_b200.so")
-SOURCES = ["api.cu", "fused_simt.cu", "fused_tc.cu", "allreduce.cu", "probe.cu"]
+SOURCES = ["api.cu", "fused_simt.cu", "fused_tc.cu", "losses.cu", "allreduce.cu", "probe.cu"]
 HEADERS = ["common.cuh", "epilogue.cuh", os.path.join("..", "..", "include", "onda_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

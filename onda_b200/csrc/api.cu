@@ -293,14 +293,13 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
                                                               const uint32_t* __restrict__ peer_done,
                                                               const uint32_t* __restrict__ peer_epoch, int peer_world) {
     __shared__ double part[8][32];
-    if (peer_done != nullptr && threadIdx.x == 0) {      // `out` is peer-visible: its previous contents must have been read
-        const uint32_t want = *peer_epoch - 1u;
+    if (peer_done != nullptr && (int)threadIdx.x < peer_world) {     // `out` is peer-visible: its previous contents must have
+        const uint32_t want = *peer_epoch - 1u;                      // been read by every rank (one flag per thread: one round trip)
         unsigned spins = 0;
-        for (int r = 0; r < peer_world; ++r)
-            while ((int)(ld_acquire_sys(peer_done + r) - want) < 0) {
-                __nanosleep(200);
-                if (++spins > 200000000u) __trap();
-            }
+        while ((int)(ld_acquire_sys(peer_done + threadIdx.x) - want) < 0) {
+            __nanosleep(200);
+            if (++spins > 200000000u) __trap();
+        }
     }
     const int el = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + el;

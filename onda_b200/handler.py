@@ -91,6 +91,7 @@ class prototype_handler:
         self._ar_calls = 0
         self.fuse_hard_soft = fuse_hard_soft
         self._stats_src = None     # (sums, C, D) of the last fused pass
+        self._local_stats = None   # same, never replaced by the all-reduced buffer
         self._stats_cache = None
         self._lib = nat.load()
         self._epoch = 0            # bumped whenever our kernels rewrite the state in place
@@ -307,6 +308,16 @@ class prototype_handler:
             self._stats_cache = self._stats_from(*src)
         return self._stats_cache or {}
 
+    def last_pixel_count(self):
+        """Device tensor (1 float) with the number of non-ignored pseudo-labels of the most recent fused pass of THIS rank
+        (the ONDA_STAT_PL_PIXELS slot of its statistics) -- what ``target_losses(..., n_valid=...)`` divides by, without
+        a device-to-host copy.  None before the first pass."""
+        src = self._local_stats
+        if src is None:
+            return None
+        sums, C, D = src
+        return sums[2 * C * D + C + nat.STAT_PL_PIXELS: 2 * C * D + C + nat.STAT_PL_PIXELS + 1]
+
     def pseudo_labels_fused(self, feat, prior, out=None, confidence_monitor=None, want_labels=True, want_soft=True):
         """Hard labels AND soft predictions from one pass over ``feat``.
 
@@ -336,6 +347,7 @@ class prototype_handler:
         labels, soft, _, sums = self._launch(feat3, prior3, logits3, self.distance_metric, want_labels, want_soft,
                                              False, C)
         self._stats_src, self._stats_cache = (sums, C, D), None
+        self._local_stats = (sums, C, D) if want_labels else self._local_stats
         monitor_live = confidence_monitor is not None and not confidence_monitor.freeze
         defer = self.process_group is not None and logits3 is not None
         if logits3 is not None:

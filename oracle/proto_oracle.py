@@ -454,6 +454,34 @@ def step_log_stats(pseudolabels: torch.Tensor, student_out: torch.Tensor, protos
     }
 
 
+def target_losses(out: torch.Tensor, labels: torch.Tensor, alpha: float, beta: float, reg_weight: float, regularizer: str):
+    """CE + RCE + regulariser on hard pseudo-labels, as online_proDA.pseudolabel_loss combines them
+    (prototypes.py:313-328).  ``out`` (B, C, h, w) logits, ``labels`` (B, h, w) int64 with 255 = ignore.
+    Restates cross_entropy_2d (framework/utils/loss.py:30-45), rce (loss.py:88-112) and regular_loss
+    (prototypes.py:29-39); differentiable through torch autograd."""
+    b, c, h, w = out.shape
+    mask = (labels >= 0) & (labels != 255)                                    # loss.py:36
+    rows = out.permute(0, 2, 3, 1)[mask]                                      # :39-41: the selected pixels' logit rows
+    ce = torch.nn.functional.cross_entropy(rows, labels[mask].long())         # :44, mean over the selection
+    p = out.softmax(dim=1)                                                    # loss.py:89
+    clone = labels.long().clone()
+    clone[clone == 255] = c                                                   # :101
+    onehot = torch.nn.functional.one_hot(clone, c + 1).float().permute(0, 3, 1, 2)[:, :-1]
+    onehot = torch.clamp(onehot, min=1e-4, max=1.0)                           # :104-106
+    m = (labels != 255).float()
+    rce_loss = -((p * torch.log(onehot)).sum(dim=1) * m).sum() / (m.sum() + 1e-6)   # :107-109
+    logp = torch.nn.functional.log_softmax(out, dim=1)                        # prototypes.py:31
+    if regularizer == "MRENT":
+        reg = (logp.exp() * logp).sum() / (b * h * w)                         # :33-35
+    elif regularizer == "MRKLD":
+        reg = -logp.sum() / (b * c * h * w)                                   # :36-39
+    else:
+        reg = out.sum() * 0
+    total = alpha * ce + beta * rce_loss + reg_weight * reg
+    agree = (labels == out.argmax(dim=1)).float().mean()                      # prototypes.py:346-347
+    return {"ce": ce, "rce": rce_loss, "reg": reg, "total": total, "agreement": agree, "n_valid": mask.sum()}
+
+
 def update_ema(params_q, params_k, buffers_q, buffers_k, ema_update: float):
     """The model-weight EMA, as written in framework/domain_adaptation/methods/prototypes.py:407-416; returns the new
     (parameter list, buffer list) of the EMA model."""

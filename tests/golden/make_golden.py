@@ -392,6 +392,29 @@ def method_variants():
                         overrides={"STATIC_LAMBDA": 1, "SWITCH_PRIOR_THRESH": 0.88})
 
 
+def losses_case():
+    """f1: the REAL cross_entropy_2d / rce (framework/utils/loss.py:16-45, 88-112) and regular_loss
+    (prototypes.py:29-39) on hard pseudo-labels, with the autograd gradient of the weighted total of
+    pseudolabel_loss (prototypes.py:313-328) with respect to the student logits."""
+    from framework.utils.loss import cross_entropy_2d, rce
+    g = torch.Generator().manual_seed(81)
+    B, C, h, w = 2, 19, 9, 13
+    out = (torch.randn(B, C, h, w, generator=g) * 2.5).requires_grad_(True)
+    lab = torch.randint(0, C, (B, h, w), generator=g)
+    lab[torch.rand(B, h, w, generator=g) < 0.3] = 255
+    res = {}
+    for reg in ("MRKLD", "MRENT"):
+        out.grad = None
+        ce = cross_entropy_2d(out, lab.long(), False)
+        r = rce(out, lab, "cpu", soft=False)
+        rg = ref_base.regular_loss(reg, out)
+        total = 0.1 * ce + 1.0 * r + 0.1 * rg                 # RCE_ALPHA, RCE_BETA, REGULARIZER_WEIGHT of the YAMLs
+        total.backward()
+        res[reg] = (ce.item(), r.item(), rg.item(), total.item(), out.grad.clone())
+    npz("target_losses.npz", out=out.detach(), labels=lab, alpha=np.float64(0.1), beta=np.float64(1.0), reg_weight=np.float64(0.1),
+        **{f"ref_{k}_{n}": v for k, (a, b, c, d, gr) in res.items() for n, v in (("ce", a), ("rce", b), ("reg", c), ("total", d), ("grad", gr))})
+
+
 def stats_case():
     """Switch statistics and the entropy map on raw logits (K4 parity)."""
     case = synth_case(61, 2, 8, 11, 17)
@@ -485,6 +508,7 @@ def main():
     stats_case()
     method_case()
     method_variants()
+    losses_case()
 
 
 if __name__ == "__main__":

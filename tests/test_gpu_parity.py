@@ -721,3 +721,66 @@ def test_confusion_meter_matches_reference_evaluation(h, w, H, W):
         meter.update(torch.zeros(1, 5, 4, 4, device=dev()), torch.zeros(1, 8, 8))
     with pytest.raises(RuntimeError, match="CUDA"):
         meter.update(torch.zeros(1, C, 4, 4), torch.zeros(1, 8, 8))
+
+
+def test_append_source_labels_matches_reference_gather_path():
+    """calculate_prototypes with STARTING_PROTO == "source" (prototypes.py:142-154): nearest-resized labels, 255 masked out,
+    class sums straight from the NCHW map -- against the reference's mask-gather + one-hot + append on the oracle."""
+    g = torch.Generator().manual_seed(71)
+    B, D, h, w, H, W, C = 3, 96, 17, 23, 129, 180, 19
+    feats = [torch.randn(B, D, h, w, generator=g) * 2 for _ in range(3)]
+    labs = []
+    for _ in range(3):
+        lab = torch.randint(0, C, (B, H, W), generator=g)
+        lab[torch.rand(B, H, W, generator=g) < 0.2] = 255
+        labs.append(lab)
+    from onda_b200 import prototype_handler
+    hd = prototype_handler(distance_metric="mahalanobis")
+    orc = po.OracleHandler(distance_metric="mahalanobis")
+    for feat, lab in zip(feats, labs):
+        # the reference's own lines, on the CPU oracle
+        labels_clone = torch.nn.functional.interpolate(lab.unsqueeze(1).float(), size=(h, w)).view(-1)
+        mask = labels_clone != 255
+        feat_clone = feat.permute(1, 0, 2, 3).reshape(D, -1)
+        rows = feat_clone[:, mask].permute(1, 0)
+        onehot = torch.nn.functional.one_hot(labels_clone[mask].long(), C)
+        orc.append(rows, onehot)
+        hd.append_source_labels(feat.to(dev()), lab.to(dev()), num_classes=C)
+    assert torch.equal(hd.counter.cpu(), orc.counter)
+    close_rel_max(hd.prototypes, orc.prototypes)
+    close_rel_max(hd.squared_mean, orc.squared_mean)
+
+
+@pytest.mark.parametrize("reg", ["MRKLD", "MRENT"])
+def test_target_losses_golden(reg):
+    """The fused CE + RCE + regulariser kernel (forward and gradient) against the real reference loss functions."""
+    from onda_b200 import target_losses
+    z = np.load(os.path.join(GOLDEN, "target_losses.npz"))
+    out = T(z["out"]).to(dev()).requires_grad_(True)
+    got = target_losses(out, T(z["labels"]).to(dev()), float(z["alpha"]), float(z["beta"]), float(z["reg_weight"]), reg)
+    got["Total target loss"].backward()
+    for ours, k in (("ce_loss", "ce"), ("rce_loss", "rce"), ("regularization_loss", "reg"), ("Total target loss", "total")):
+        assert float(got[ours]) == pytest.approx(float(z[f"ref_{reg}_{k}"]), rel=2e-6), k
+    gref = T(z[f"ref_{reg}_grad"])
+    assert float((out.grad.cpu() - gref).abs().max()) <= 1e-5 * float(gref.abs().max())
+
+
+def test_target_losses_full_size_against_oracle():
+    """Config-3 sized logits (32 x 19 x 65 x 129) with the labels and the device-side label count of a fused pass."""
+    from onda_b200 import target_losses
+    case = po.synth_case(91, 8, 64, 65, 129)
+    hd = make_handler(case["protos"], case["sq_mean"], case["counter"], "mahalanobis")
+    labels, _ = hd.pseudo_labels_fused(case["feat"].to(dev()), case["prior"].to(dev()), case["out"].to(dev()))
+    g = torch.Generator().manual_seed(92)
+    student = torch.randn(8, 19, 65, 129, generator=g) * 3
+    ref_in = student.clone().requires_grad_(True)
+    ref = po.target_losses(ref_in, labels.cpu().view(8, 65, 129), 0.1, 1.0, 0.1, "MRKLD")
+    ref["total"].backward()
+    out = student.to(dev()).requires_grad_(True)
+    got = target_losses(out, labels, 0.1, 1.0, 0.1, "MRKLD", n_valid=hd.last_pixel_count())
+    (2.0 * got["Total target loss"]).backward()                       # upstream gradient != 1
+    assert float(got["pseudolabel_pixel_num"]) == float(ref["n_valid"])
+    assert float(got["output & prototype agreement"]) == pytest.approx(float(ref["agreement"]), abs=1e-7)
+    for ours, k in (("ce_loss", "ce"), ("rce_loss", "rce"), ("regularization_loss", "reg"), ("Total target loss", "total")):
+        assert float(got[ours]) == pytest.approx(float(ref[k]), rel=1e-5), k
+    assert float((out.grad.cpu() - 2.0 * ref_in.grad).abs().max()) <= 1e-5 * float(2.0 * ref_in.grad.abs().max())

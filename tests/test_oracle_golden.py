@@ -177,3 +177,15 @@ def test_hswitch_share_restatement_matches_reference_trace(fixture):
         share = static_share(mon.avg("prior static"), bool(int(z["soft_trans"])), float(z["switch_prior_thresh"]))
         assert share == float(z["ref_share"][i]), i
         assert po.hswitch_percentage(mon.avg("prior static"), bool(int(z["soft_trans"])), float(z["switch_prior_thresh"])) == share
+
+
+@pytest.mark.parametrize("reg", ["MRKLD", "MRENT"])
+def test_target_losses_restatement_matches_reference(reg):
+    """oracle.target_losses against the REAL cross_entropy_2d / rce / regular_loss and their autograd gradient."""
+    z = np.load(os.path.join(GOLDEN, "target_losses.npz"))
+    out = torch.from_numpy(z["out"]).requires_grad_(True)
+    got = po.target_losses(out, torch.from_numpy(z["labels"]), float(z["alpha"]), float(z["beta"]), float(z["reg_weight"]), reg)
+    got["total"].backward()
+    for k in ("ce", "rce", "reg", "total"):
+        assert got[k].item() == pytest.approx(float(z[f"ref_{reg}_{k}"]), rel=1e-6, abs=1e-7), k
+    np.testing.assert_allclose(out.grad.numpy(), z[f"ref_{reg}_grad"], rtol=1e-5, atol=1e-8)
