@@ -364,22 +364,22 @@ __global__ void counter_add_kernel(float* __restrict__ counter, const float* __r
 constexpr int kPriorThreads = 256;
 
 template <int CP>
-__global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* __restrict__ l0, const float* __restrict__ l1,
-                                                                  const float* __restrict__ l2, float c0, float c1, float c2,
-                                                                  float scale01, int B, int C, int HW, float* __restrict__ prior_out,
-                                                                  float* __restrict__ partials, unsigned* __restrict__ ticket,
-                                                                  float* __restrict__ stats_out) {
+__global__ void __launch_bounds__(kPriorThreads, CP == 20 ? 4 : 2) prior_mix_kernel(const float* __restrict__ l0, const float* __restrict__ l1,
+                                                                     const float* __restrict__ l2, float c0, float c1, float c2,
+                                                                     float scale01, int B, int C, int HW, float* __restrict__ prior_out,
+                                                                     float* __restrict__ partials, unsigned* __restrict__ ticket,
+                                                                     float* __restrict__ stats_out) {
     __shared__ float red[kPriorThreads / 32][kStatSlots];
     __shared__ bool last;
-    const long long N = (long long)B * HW;
+    const unsigned N = (unsigned)B * (unsigned)HW, hw = (unsigned)HW;       // 32-bit indices (the host checks B*C*HW < 2^32)
     const float* src[3] = {l0, l1, l2};
     const float coef[3] = {c0, c1, c2};
     float st[kStatSlots];
 #pragma unroll
     for (int s = 0; s < kStatSlots; ++s) st[s] = 0.f;
-    for (long long n = (long long)blockIdx.x * kPriorThreads + threadIdx.x; n < N; n += (long long)gridDim.x * kPriorThreads) {
-        const long long b = n / HW, q = n - b * HW;
-        const long long off = (b * C) * (long long)HW + q;
+    for (unsigned n = blockIdx.x * kPriorThreads + threadIdx.x; n < N; n += gridDim.x * kPriorThreads) {
+        const unsigned b = n / hw, q = n - b * hw;
+        const unsigned off = (b * (unsigned)C) * hw + q;
         float mix[CP];
 #pragma unroll
         for (int k = 0; k < CP; ++k) mix[k] = 0.f;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* _
 #pragma unroll
             for (int k = 0; k < CP; ++k) {
                 if (k < C) {
-                    z[k] = __ldg(src[i] + off + (long long)k * HW);
+                    z[k] = __ldg(src[i] + off + (unsigned)k * hw);
                     if (z[k] > zmax || z[k] != z[k]) zmax = z[k];
                 }
             }
@@ -405,15 +405,16 @@ __global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* _
 #pragma unroll
             for (int k = 0; k < CP; ++k) {
                 if (k < C) {
-                    z[k] = exp2f((z[k] - zmax) * 1.4426950408889634f);
+                    z[k] = fast_ex2((z[k] - zmax) * 1.4426950408889634f);    // single MUFU, 2^-22 relative
                     esum += z[k];
                 }
             }
+            const float inv = __frcp_rn(esum);            // one rounded reciprocal per pixel instead of C divisions (<= 1 ulp apart)
             float pmax = -1.f;
 #pragma unroll
             for (int k = 0; k < CP; ++k) {
                 if (k < C) {
-                    const float pk = __fdiv_rn(z[k], esum);   // softmax(axis=1), prototypes_hybrid_switch.py:53
+                    const float pk = __fmul_rn(z[k], inv);    // softmax(axis=1), prototypes_hybrid_switch.py:53
                     if (torch_greater(pk, pmax)) pmax = pk;
                     mix[k] = __fadd_rn(mix[k], __fmul_rn(coef[i], pk));  // prior (+)= lambda * softmax, :56, :64, :84
                 }
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(kPriorThreads) prior_mix_kernel(const float* _
         for (int k = 0; k < CP; ++k) {
             if (k < C) {
                 if (torch_greater(mix[k], mmax)) mmax = mix[k];
-                if (prior_out != nullptr) prior_out[off + (long long)k * HW] = mix[k];
+                if (prior_out != nullptr) prior_out[off + (unsigned)k * hw] = mix[k];
             }
         }
         st[3] += mmax;                                        // {"prior": prior.max(axis=1)[0].mean()}, :88
@@ -966,7 +967,7 @@ int onda_append_update(float* prototypes, float* squared_mean, float* counter, c
 
 size_t onda_prior_workspace_bytes(int B, int C, int HW) {
     (void)B; (void)C; (void)HW;
-    return 256 + (size_t)4 * cached_sm_count() * kStatSlots * sizeof(float);
+    return 256 + (size_t)8 * cached_sm_count() * kStatSlots * sizeof(float);
 }
 
 int onda_prior_mix_stats(const float* logits0, const float* logits1, const float* logits2, float coef0, float coef1,
@@ -974,12 +975,13 @@ int onda_prior_mix_stats(const float* logits0, const float* logits1, const float
                          void* workspace, size_t workspace_bytes, void* stream) {
     ONDA_REQUIRE(stats_out && workspace, "onda_prior_mix_stats: null stats/workspace");
     ONDA_REQUIRE(logits0 || logits1 || logits2, "onda_prior_mix_stats: no input");
-    ONDA_REQUIRE(B > 0 && HW > 0 && C > 0 && C <= ONDA_MAX_CLASSES, "onda_prior_mix_stats: bad shape");
+    ONDA_REQUIRE(B > 0 && HW > 0 && C > 0 && C <= ONDA_MAX_CLASSES && (unsigned long long)B * C * HW < (1ull << 32),
+                 "onda_prior_mix_stats: bad shape");
     ONDA_REQUIRE(workspace_bytes >= onda_prior_workspace_bytes(B, C, HW), "onda_prior_mix_stats: workspace too small");
     const long long N = (long long)B * HW;
     const int sms = cached_sm_count();
     long long want = (N + kPriorThreads - 1) / kPriorThreads;
-    const int grid = (int)(want < 4LL * sms ? want : 4LL * sms);
+    const int grid = (int)(want < 8LL * sms ? want : 8LL * sms);
     unsigned* ticket = (unsigned*)workspace;  // zero on first use; the kernel re-arms it
     float* partials = (float*)((char*)workspace + 256);
     if (padded_classes(C) == 20)

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(kLossThreads) count_valid_kernel(const long lo
 }
 
 template <int CP>
-__global__ void __launch_bounds__(kLossThreads) target_loss_kernel(const float* __restrict__ logits,
+__global__ void __launch_bounds__(kLossThreads, CP == 20 ? 3 : 2) target_loss_kernel(const float* __restrict__ logits,
                                                                    const long long* __restrict__ labels, int B, int C, int HW,
                                                                    const float* __restrict__ n_valid_f,
                                                                    const unsigned long long* __restrict__ n_valid_u,
@@ -39,23 +39,23 @@ __global__ void __launch_bounds__(kLossThreads) target_loss_kernel(const float* 
                                                                    unsigned* __restrict__ ticket, float* __restrict__ out) {
     __shared__ double red[kLossThreads / 32][kLossSlots];
     __shared__ bool last;
-    const long long N = (long long)B * HW;
+    const unsigned N = (unsigned)B * (unsigned)HW, hw = (unsigned)HW;        // 32-bit indices (the host checks B*C*HW < 2^32)
     const float nv = n_valid_f != nullptr ? *n_valid_f : (float)*n_valid_u;
     const float log_floor = 9.210340371976182f;            // -log(1e-4): the clamp of the one-hot target (loss.py:104-106)
     const float g_ce = alpha / nv;                          // F.cross_entropy(..., size_average=True) over the selected pixels
     const float g_rce = beta * log_floor / (nv + 1e-6f);
     const float g_reg = reg_kind == ONDA_REG_MRKLD ? reg_weight / ((float)N * (float)C) : reg_weight / (float)N;
     double ce = 0.0, rce = 0.0, reg = 0.0, agree = 0.0;
-    for (long long n = (long long)blockIdx.x * kLossThreads + threadIdx.x; n < N; n += (long long)gridDim.x * kLossThreads) {
-        const long long b = n / HW, q = n - b * HW;
-        const long long off = (b * C) * (long long)HW + q;
+    for (unsigned n = blockIdx.x * kLossThreads + threadIdx.x; n < N; n += gridDim.x * kLossThreads) {
+        const unsigned b = n / hw, q = n - b * hw;
+        const unsigned off = (b * (unsigned)C) * hw + q;
         float z[CP];
         float zmax = -__int_as_float(0x7f800000);
         int arg = 0;
 #pragma unroll
         for (int k = 0; k < CP; ++k)
             if (k < C) {
-                z[k] = __ldg(logits + off + (long long)k * HW);
+                z[k] = __ldg(logits + off + (unsigned)k * hw);
                 if (torch_greater(z[k], zmax)) { zmax = z[k]; arg = k; }
             }
         float esum = 0.f;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kLossThreads) target_loss_kernel(const float* 
                     }
                     if (reg_kind == ONDA_REG_MRKLD) gk += g_reg * ((float)C * p[k] - 1.f);
                     else if (reg_kind == ONDA_REG_MRENT) gk += g_reg * p[k] * ((z[k] - lse) - plogp);
-                    grad[off + (long long)k * HW] = gk;
+                    grad[off + (unsigned)k * hw] = gk;
                 }
         }
     }
@@ -141,21 +141,22 @@ using namespace onda;
 
 extern "C" {
 
-size_t onda_target_loss_workspace_bytes(void) { return 512 + (size_t)4 * cached_sm_count() * kLossSlots * sizeof(double); }
+size_t onda_target_loss_workspace_bytes(void) { return 512 + (size_t)8 * cached_sm_count() * kLossSlots * sizeof(double); }
 
 int onda_target_loss_fused(const float* student_logits, const int64_t* labels, int B, int C, int HW, const float* n_valid,
                            float alpha, float beta, float reg_weight, int regularizer, float* grad, float* out6,
                            void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     ONDA_REQUIRE(student_logits && labels && out6 && workspace, "onda_target_loss_fused: null pointer");
-    ONDA_REQUIRE(B > 0 && HW > 0 && C > 0 && C <= ONDA_MAX_CLASSES, "onda_target_loss_fused: bad shape");
+    ONDA_REQUIRE(B > 0 && HW > 0 && C > 0 && C <= ONDA_MAX_CLASSES && (unsigned long long)B * C * HW < (1ull << 32),
+                 "onda_target_loss_fused: bad shape");
     ONDA_REQUIRE(regularizer == ONDA_REG_NONE || regularizer == ONDA_REG_MRKLD || regularizer == ONDA_REG_MRENT,
                  "onda_target_loss_fused: unknown regularizer %d", regularizer);
     ONDA_REQUIRE(workspace_bytes >= onda_target_loss_workspace_bytes(), "onda_target_loss_fused: workspace too small");
     const long long N = (long long)B * HW;
     const int sms = cached_sm_count();
     long long want = (N + kLossThreads - 1) / kLossThreads;
-    const int grid = (int)(want < 4LL * sms ? want : 4LL * sms);
+    const int grid = (int)(want < 8LL * sms ? want : 8LL * sms);
     unsigned* ticket = (unsigned*)workspace;                                   // zero on first use; the kernel re-arms it
     unsigned long long* count = (unsigned long long*)((char*)workspace + 256);
     double* partials = (double*)((char*)workspace + 512);
