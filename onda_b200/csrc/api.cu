@@ -845,6 +845,7 @@ int onda_pseudolabel_fused_guarded(const float* feat, const float* prior, const 
     int n_cta, n_stat;
     if (use_tc) {
         p.tiles_per_img = (HW + kTilePixels - 1) / kTilePixels;
+        p.sched = reinterpret_cast<unsigned*>(const_cast<float*>(table) + table_layout(C, D).off_sched);
         p.tiles = tc_tiles(B, HW);
         const int slices = tc_slices(p.tiles, D, sms);
         p.nslices = slices; p.slice_channels = D / slices; p.cluster = 1;

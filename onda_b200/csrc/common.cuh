@@ -53,8 +53,9 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 // Dp = D rounded up to 32; padded channels carry w = 0, Q = 0 so they contribute nothing.
 struct TableLayout {
     int C, D, Dp, CP, BR;
-    size_t off_sigma, off_w, off_mu, off_bias, off_q, off_b, off_scratch, total;
+    size_t off_sigma, off_w, off_mu, off_bias, off_q, off_b, off_scratch, off_sched, total;
 };
+constexpr int kTcSchedSlices = 16;      // tile counters of the tcgen05 kernel: one per channel slice, then the exit ticket
 __host__ __device__ inline TableLayout table_layout(int C, int D) {
     TableLayout t;
     t.C = C; t.D = D; t.Dp = round_up(D, 32); t.CP = padded_classes(C); t.BR = C <= 24 ? 24 : 32;
@@ -65,7 +66,8 @@ __host__ __device__ inline TableLayout table_layout(int C, int D) {
     t.off_q = t.off_bias + 32;
     t.off_b = t.off_q + (size_t)t.Dp * t.CP;
     t.off_scratch = t.off_b + (size_t)2 * t.BR * t.Dp + 64;      // (+ 64: the over-read of the last slab stays inside the table); per-CTA bias partials (doubles) + ticket of the table kernel
-    t.total = t.off_scratch + (size_t)2 * 32 * (t.Dp / 32) + 8;
+    t.off_sched = t.off_scratch + (size_t)2 * 32 * (t.Dp / 32) + 8;      // zero between launches (re-armed by the kernel that uses them)
+    t.total = t.off_sched + kTcSchedSlices + 8;
     return t;
 }
 

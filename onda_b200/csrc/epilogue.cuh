@@ -22,6 +22,7 @@ struct FusedParams {
     float* cta_partials;   // [gridDim.x][sums_floats(C, D)] class sums / counts (stats slots unused)
     float* stat_partials;  // [n_stat_ctas][kStatSlots]
     float* dots_scratch;   // [nslices][CP + 1][N] partial dot products when nslices > 1
+    unsigned* sched;       // tile counters of the tcgen05 kernel (inside the distance table, TableLayout::off_sched)
     int nslices;           // channel slices (gridDim.y)
     int slice_channels;    // channels per slice, multiple of 32
     int tiles;             // CUDA-core kernel: ceil(N / 128) tiles of the flattened pixel axis; tcgen05 kernel: B * tiles_per_img
@@ -107,6 +108,9 @@ __device__ __forceinline__ int first_argmax_fast(const float (&v)[CP], int C) {
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// NaN-propagating min / max (one FMNMX each): what `(a < b || a != a) ? a : b` spells with two compares and a select
+__device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // Everything after the squared distances for one pixel (one thread).  Follows
@@ -126,11 +130,9 @@ __device__ __forceinline__ void rectify_pixel(float (&v)[CP], const float (&pri)
 #pragma unroll
     for (int k = 0; k < CP; ++k) {
         if (k < C) {
-            float x = v[k];
-            x = x < 0.f ? 0.f : x;              // rounding can make a ~0 squared distance negative; keeps NaN
-            const float d = fast_sqrt(x);
+            const float d = fast_sqrt(fmax_nan(v[k], 0.f));      // rounding can make a ~0 squared distance negative; keeps NaN
             v[k] = d;
-            dmin = (d < dmin || d != d) ? d : dmin;
+            dmin = fmin_nan(d, dmin);                            // a NaN distance makes the whole row NaN, like torch.min
             dmax = fmaxf(dmax, d);
         }
     }

@@ -76,6 +76,7 @@ constexpr int kTcChunkC = 32;                    // channels per chunk
 constexpr int kTcRowBytes = 528;                 // 16-byte cover of 128 floats at any 4-byte phase
 constexpr int kTcStageBytes = kTcChunkC * kTcRowBytes;
 constexpr int kTcMaxStages = 8;
+constexpr int kTcTileQ = 16;                    // tile queue slots (a power of two, more than the roles can drift apart)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = kTcAStages * 64;   // accumulators after the A stages
 constexpr uint32_t kAccSet = 96;                 // per tile parity: three accumulators of 32 columns (one per term of the split, so
@@ -251,7 +252,7 @@ __host__ __device__ constexpr int ring_slot(int j) { return 8 * (j & 3) + (j >> 
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------
 struct TcSmem {
-    size_t bars, tmem_ptr, eoff, ecls, cuts, wc, cnt, red, out, mu, w, btab, acc, ring, total;  // byte offsets
+    size_t bars, tmem_ptr, tq, bias, eoff, ecls, cuts, wc, cnt, red, out, mu, w, btab, acc, ring, total;  // byte offsets
     int nstage;
 };
 __host__ __device__ inline TcSmem tc_smem(int Dc, int C, int CP, bool sums, int nstage) {
@@ -260,14 +261,16 @@ __host__ __device__ inline TcSmem tc_smem(int Dc, int C, int CP, bool sums, int 
     // shared-memory base and cost no registers.
     TcSmem s;
     size_t o = 0;
-    s.bars = o; o += 384;                              // 2 * kTcMaxStages + 2 * kTcAStages + 9 mbarriers
-    s.tmem_ptr = o; o += 128;
+    s.bars = o; o += 512;                              // 2 * kTcMaxStages + 2 * kTcAStages + 9 + kTcTileQ mbarriers
+    s.tmem_ptr = o; o += 64;
+    s.tq = o; o += 64;                                 // tile queue: the tile of this CTA's t-th step, slot t % kTcTileQ (-1: no more)
     s.eoff = o; o += (size_t)2 * kTilePixels * 4;      // per tile parity: row offset of every class-sorted entry | segment-end flag
     s.ecls = o; o += (size_t)2 * kTilePixels * 4;      // ... and its accumulator row (class * Dc; -1 = head segment of its range)
     s.cuts = o; o += 128;                              // ... [0] live entries, [1..3] the classes cut by the range starts 32, 64, 96
     s.wc = o; o += 640;                                // per-warp class histograms of the sorter (4 x 36)
     s.cnt = o; o += 128;
     s.red = o; o += 4 * kStatSlots * 4;
+    s.bias = o; o += 128;                              // per-class bias of the distance (TableLayout::off_bias)
     s.out = o; o += (size_t)kTilePixels * (CP + 1) * 4;
     o = (o + 127) / 128 * 128;
     s.mu = o; o += (size_t)Dc * 4;
@@ -331,9 +334,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     auto sort_ready = [&](int i) { return bars + 8u * (kB0 + 2 * kTcAStages + 4 + i); };
     auto sort_free = [&](int i) { return bars + 8u * (kB0 + 2 * kTcAStages + 6 + i); };
     const uint32_t btab_bar = bars + 8u * (kB0 + 2 * kTcAStages + 8);
+    auto tq_full = [&](int s) { return bars + 8u * (kB0 + 2 * kTcAStages + 9 + s); };
+    volatile int* tq = reinterpret_cast<volatile int*>(smem_raw + L.tq);
 
     const TableLayout T = table_layout(C, D);
     // ---- one-time setup: tables to shared memory, barriers, tensor memory
+    float* bias_s = reinterpret_cast<float*>(smem_raw + L.bias);
+    if (tid < 32) bias_s[tid] = tid < C ? p.table[T.off_bias + tid] : 0.f;
     for (int i = tid; i < Dc; i += kTcThreads) {
         mus[i] = -p.table[T.off_mu + c_base + i];      // negated: the converters centre with a packed add
         wsm[i] = p.table[T.off_w + c_base + i];
@@ -343,6 +350,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         if (tid < 32) cnt[tid] = 0;
     }
     if (tid == 0) {
+        {   // B operand table of this CTA's channel slice: one bulk asynchronous copy, issued first and off everybody's
+            // critical path -- only the MMA issuer waits for it, before its first MMA
+            mbar_init(btab_bar, 1);
+            fence_barrier_init();
+            const uint32_t bytes = (uint32_t)(2 * T.BR * Dc) * 4u;
+            mbar_arrive_tx(btab_bar, bytes);
+            bulk_g2s_plain(smem_u32(Btab), p.table + T.off_b + (size_t)c_base * 2 * T.BR, bytes, btab_bar);
+        }
         for (int s = 0; s < nstage; ++s) {
             mbar_init(ring_full(s), 1);                  // the producer's expect_tx arrive; the four tensor copies complete the bytes
             mbar_init(ring_empty(s), SUMS ? 8 : 4);      // the four converter warps and the four summer warps of the chunk
@@ -357,13 +372,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             mbar_init(sort_ready(i), 64);
             mbar_init(sort_free(i), 4 * (NB < kTcSumGroups ? NB : kTcSumGroups));   // the summer warps that have chunks
         }
-        mbar_init(btab_bar, 1);
+        for (int i = 0; i < kTcTileQ; ++i) mbar_init(tq_full(i), 1);
         fence_barrier_init();
-        // B operand table of this CTA's channel slice: one bulk asynchronous copy, off everybody's critical path -- only
-        // the MMA issuer waits for it, before its first MMA
-        const uint32_t bytes = (uint32_t)(2 * T.BR * Dc) * 4u;
-        mbar_arrive_tx(btab_bar, bytes);
-        bulk_g2s_plain(smem_u32(Btab), p.table + T.off_b + (size_t)c_base * 2 * T.BR, bytes, btab_bar);
     }
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
@@ -378,12 +388,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_start = PROF ? clock64() : 0;
     const unsigned tpi = (unsigned)p.tiles_per_img;
-    const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_chunks = my_tiles * NB;
     const unsigned HWu = (unsigned)HW;
-    // tile t of this CTA -> image, first pixel, live pixels
-    auto tile_of = [&](int t, unsigned& img, unsigned& pix0, int& npx) {
-        const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
+    // Tiles are handed out dynamically (the producer draws them from a global counter two steps ahead and publishes
+    // them in the queue): SMs do not run at the same speed, and tiles / SMs is rarely an integer.  The tile of this
+    // CTA's t-th step, or -1 when there is none:
+    auto tile_at = [&](int t) -> int {
+        mbar_wait(tq_full(t & (kTcTileQ - 1)), ((uint32_t)t / kTcTileQ) & 1);
+        return tq[t & (kTcTileQ - 1)];
+    };
+    // tile -> image, first pixel, live pixels
+    auto tile_of = [&](int tile_, unsigned& img, unsigned& pix0, int& npx) {
+        const unsigned tile = (unsigned)tile_;
         img = tile / tpi;
         pix0 = (tile - img * tpi) * kTilePixels;
         const unsigned rem = HWu - pix0;
@@ -401,8 +416,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         uint32_t rphase = 0;
         int t = 0, blk = group;
         float x[kTcChunkC];
-        for (int q = group; q < total_chunks; q += kTcConvGroups) {
-            while (blk >= NB) { blk -= NB; ++t; }
+        for (int q = group;; q += kTcConvGroups) {
+            if (blk >= NB) { blk -= NB; ++t; }               // NB is even and >= 2: one tile at most
+            if (blk < kTcConvGroups && tile_at(t) < 0) break;     // the group's first chunk of a tile: is there a tile?
             const int par = t & 1;
             const int as = q & (kTcAStages - 1);
             const uint32_t use = (uint32_t)q >> 2;
@@ -483,7 +499,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         const uint32_t lane_off = (uint32_t)ring_slot(lane) * kTcRowBytes + 4u * (uint32_t)maps.shift[lane & 3];   // pixel 0 of this lane's channel row
         const int idx = 32 * quarter + lane;                // this warp's range: entries 32*quarter .. +31
         const bool single = group + kTcSumGroups >= NB;     // one chunk per tile: consecutive chunks of the group share their accumulator rows
-        for (int t = 0; t < my_tiles; ++t)
+        for (int t = 0; tile_at(t) >= 0; ++t)
         for (int blk = group; blk < NB; blk += kTcSumGroups, hp ^= 1) {
             {   // ring stage of chunk q = t * NB + blk
                 const int q = t * NB + blk;
@@ -606,12 +622,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         const int et = tid - kTcEpiWarp0 * 32;          // 0..127 = pixel row of the tile = TMEM lane
         const uint32_t lane_base = (uint32_t)(et & ~31) << 16;
         PixelStats st;
-        const float* bias = p.table + T.off_bias;
-        for (int t = 0; t < my_tiles; ++t) {
+        for (int t = 0;; ++t) {
+            const int tile = tile_at(t);
+            if (tile < 0) break;
             const int par = t & 1;
             unsigned img, pix0;
             int npx;
-            tile_of(t, img, pix0, npx);
+            tile_of(tile, img, pix0, npx);
             const long long n0 = (long long)img * HW + pix0;
             float pri[CP];
             {   // prior row of this pixel: issued before the wait so its latency hides behind the MMAs
@@ -657,7 +674,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < CP; ++k) d2[k] = (a_tot + __ldg(bias + k)) + (d2[k] + __uint_as_float(dv[k]));
+                for (int k = 0; k < CP; ++k) d2[k] = (a_tot + bias_s[k]) + (d2[k] + __uint_as_float(dv[k]));
                 finish_pixel_rows<CP, WANT_DIST>(p, C, d2, n0, npx, et, out_stage, st, pri);
             }
         }
@@ -691,7 +708,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const uint32_t kstep = 4u * (uint32_t)T.BR;      // one K-step = 8 channels = two slabs, in the descriptor's 16-byte units
             mbar_wait(btab_bar, 0);             // the B table has landed (bulk copy of the prologue)
             int q = 0;
-            for (int t = 0; t < my_tiles; ++t) {
+            for (int t = 0; tile_at(t) >= 0; ++t) {
                 const int par = t & 1;
                 if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
                 const uint32_t d0 = tmem_base + kAccCol0 + (uint32_t)par * kAccSet, d1 = d0 + 64;
@@ -736,10 +753,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             for (int r = 0; r < 4; ++r) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.map[r]) : "memory");
             int stage = 0;
             uint32_t rphase = 0;
-            for (int t = 0; t < my_tiles; ++t) {
+            // Tile schedule: steps 0 and 1 are static (tiles blockIdx.x and blockIdx.x + gridDim.x), later ones are drawn
+            // from this slice's counter while the copies of two steps earlier are being issued, and published one step
+            // before anybody needs them (the sorter reads one step ahead).  The last CTA to leave re-arms the counters.
+            const int G = (int)gridDim.x;
+            unsigned* counter = p.sched + blockIdx.y;
+            int cur = (int)blockIdx.x, nxt = (int)blockIdx.x + G < p.tiles ? (int)blockIdx.x + G : -1;
+            tq[0] = cur;
+            tq[1] = nxt;
+            mbar_arrive(tq_full(0));
+            mbar_arrive(tq_full(1));
+            for (int t = 0; cur >= 0; ++t) {
+                int after = -1;
+                if (nxt >= 0) after = 2 * G + (int)atomicAdd(counter, 1u);
                 unsigned img, pix0;
                 int npx;
-                tile_of(t, img, pix0, npx);
+                tile_of(cur, img, pix0, npx);
                 for (int b = 0; b < NB; ++b) {
                     mbar_wait_t(ring_empty(stage), rphase ^ 1, prof, dbg[0]);
                     const uint32_t dst = ring + (uint32_t)stage * kTcStageBytes;
@@ -751,6 +780,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                                     (int)img, bar, policy);
                     if (++stage == nstage) { stage = 0; rphase ^= 1; }
                 }
+                if (after >= p.tiles) after = -1;
+                tq[(t + 2) & (kTcTileQ - 1)] = after;
+                mbar_arrive(tq_full((t + 2) & (kTcTileQ - 1)));
+                cur = nxt;
+                nxt = after;
             }
         }
         __syncwarp();
@@ -764,21 +798,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         const int sw = warp - kTcSortWarp0;
         float lv[2][CP];
         auto fetch_logits = [&](int t) {   // the logits of tile t+1 are fetched while tile t is being sorted
-            if (t >= my_tiles) return;
+            const int tile = tile_at(t);
+            if (tile < 0) return;
             unsigned img, pix0;
             int npx;
-            tile_of(t, img, pix0, npx);
+            tile_of(tile, img, pix0, npx);
             const float* lp = p.logits + ((size_t)img * C) * HW + pix0 + 64 * sw + lane;
             if (64 * sw + lane < npx) load_pixel_row_at<CP>(lp, C, HWu, lv[0]);
             if (64 * sw + 32 + lane < npx) load_pixel_row_at<CP>(lp + 32, C, HWu, lv[1]);
         };
         fetch_logits(0);
         const unsigned lt_mask = (1u << lane) - 1u;
-        for (int t = 0; t < my_tiles; ++t) {
+        for (int t = 0;; ++t) {
+            const int tile = tile_at(t);
+            if (tile < 0) break;
             const int par = t & 1;
             unsigned img, pix0;
             int npx;
-            tile_of(t, img, pix0, npx);
+            tile_of(tile, img, pix0, npx);
             int y[2], bucket[2];
             unsigned peers[2];
 #pragma unroll
@@ -853,12 +890,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     const long long t_sync_end = PROF ? clock64() : 0;
     if (SUMS) {
         float* out = p.cta_partials + (size_t)blockIdx.x * sums_floats(C, D);
-        const int cd = C * Dc;
-        for (int i = tid; i < 2 * cd; i += kTcThreads) {     // out: [sum | sum of squares][class][D]
-            const int stat = i >= cd, rem = i - stat * cd, k = rem / Dc, j = rem - k * Dc;
-            out[(size_t)(stat * C + k) * D + c_base + j] = acc[((k * NB + (j >> 5)) * 2 + stat) * 32 + (j & 31)];
+        // accumulator row r = (class * NB + chunk) * 2 + statistic, 32 channels -> out: [sum | sum of squares][class][D]
+        const unsigned inv_nb = (65536u + (unsigned)NB - 1u) / (unsigned)NB;      // kc / NB = (kc * inv_nb) >> 16 for kc < 2^13
+        for (int r = warp; r < 2 * C * NB; r += kTcThreads / 32) {
+            const int stat = r & 1, kc = r >> 1;
+            const int k = (int)(((unsigned)kc * inv_nb) >> 16), chunk = kc - k * NB;
+            out[(size_t)(stat * C + k) * D + c_base + chunk * 32 + lane] = acc[r * 32 + lane];
         }
         if (tid < C && blockIdx.y == 0) out[(size_t)2 * C * D + tid] = (float)cnt[tid];
+    }
+    if (tid == 0) {      // every CTA has drawn its last tile: the last one to leave zeroes the counters for the next launch
+        __threadfence();
+        const unsigned n_cta = gridDim.x * gridDim.y;
+        if (atomicAdd(p.sched + kTcSchedSlices, 1u) == n_cta - 1) {
+            __threadfence();
+            for (unsigned y = 0; y < gridDim.y; ++y) p.sched[y] = 0u;
+            p.sched[kTcSchedSlices] = 0u;
+        }
     }
     if (warp == kTcMmaWarp) {
         tc_fence_after();
