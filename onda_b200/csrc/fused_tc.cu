@@ -755,9 +755,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             uint32_t rphase = 0;
             // Tile schedule: steps 0 and 1 are static (tiles blockIdx.x and blockIdx.x + gridDim.x), later ones are drawn
             // from this slice's counter while the copies of two steps earlier are being issued, and published one step
-            // before anybody needs them (the sorter reads one step ahead).  The last CTA to leave re-arms the counters.
+            // before anybody needs them (the sorter reads one step ahead).
             const int G = (int)gridDim.x;
             unsigned* counter = p.sched + blockIdx.y;
+            const bool drawing = p.tiles > 2 * G;          // else every tile is one of the static two per CTA
             int cur = (int)blockIdx.x, nxt = (int)blockIdx.x + G < p.tiles ? (int)blockIdx.x + G : -1;
             tq[0] = cur;
             tq[1] = nxt;
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             mbar_arrive(tq_full(1));
             for (int t = 0; cur >= 0; ++t) {
                 int after = -1;
-                if (nxt >= 0) after = 2 * G + (int)atomicAdd(counter, 1u);
+                if (nxt >= 0 && drawing) after = 2 * G + (int)atomicAdd(counter, 1u);
                 unsigned img, pix0;
                 int npx;
                 tile_of(cur, img, pix0, npx);
@@ -785,6 +786,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 mbar_arrive(tq_full((t + 2) & (kTcTileQ - 1)));
                 cur = nxt;
                 nxt = after;
+            }
+            // This CTA has drawn its last tile.  The last producer to get here zeroes the counters for the next launch
+            // (launches that never draw -- every tile assigned statically -- skip the ticket).
+            if (drawing) {
+                __threadfence();
+                if (atomicAdd(p.sched + kTcSchedSlices, 1u) == gridDim.x * gridDim.y - 1) {
+                    __threadfence();
+                    for (unsigned y = 0; y < gridDim.y; ++y) p.sched[y] = 0u;
+                    p.sched[kTcSchedSlices] = 0u;
+                }
             }
         }
         __syncwarp();
@@ -898,15 +909,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             out[(size_t)(stat * C + k) * D + c_base + chunk * 32 + lane] = acc[r * 32 + lane];
         }
         if (tid < C && blockIdx.y == 0) out[(size_t)2 * C * D + tid] = (float)cnt[tid];
-    }
-    if (tid == 0) {      // every CTA has drawn its last tile: the last one to leave zeroes the counters for the next launch
-        __threadfence();
-        const unsigned n_cta = gridDim.x * gridDim.y;
-        if (atomicAdd(p.sched + kTcSchedSlices, 1u) == n_cta - 1) {
-            __threadfence();
-            for (unsigned y = 0; y < gridDim.y; ++y) p.sched[y] = 0u;
-            p.sched[kTcSchedSlices] = 0u;
-        }
     }
     if (warp == kTcMmaWarp) {
         tc_fence_after();
