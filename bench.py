@@ -285,7 +285,7 @@ def run_onda(args):
     if world > 1:   # identical prototypes everywhere
         for t in (protos, sq_mean, counter):
             dist.broadcast(t, 0)
-    h = prototype_handler(process_group=group, impl=args.kernel, allreduce=args.allreduce, **PARAMS)
+    h = prototype_handler(process_group=group, impl=args.kernel, allreduce=args.allreduce, tile_schedule=args.tile_schedule, **PARAMS)
     h.prototypes, h.squared_mean, h.counter = protos.clone(), sq_mean.clone(), counter.clone()
 
     def step(i):
@@ -389,7 +389,7 @@ def run_onda(args):
             gathered.append(parts)
         relerr = None
         if rank == 0:
-            h1 = prototype_handler(impl=args.kernel, **PARAMS)
+            h1 = prototype_handler(impl=args.kernel, tile_schedule=args.tile_schedule, **PARAMS)
             h1.prototypes, h1.squared_mean, h1.counter = (t.clone() for t in start)
             for i in range(2):
                 feat, prior, out = gathered[i]
@@ -462,6 +462,7 @@ def run_onda(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(d, world, args),
         "launch_mode": "CUDA graph replay (one graph per input set)" if graphs is not None else "eager launches",
+        "tile_schedule": args.tile_schedule,
         "input_sets": len(sets),
         "exchange": (None if world == 1 else
                      {"requested": args.allreduce, "effective": h.allreduce,
@@ -504,6 +505,8 @@ def main():
                     help="exchange of the class-sum buffer at N>1: NCCL all_reduce or the library's one-shot NVLink kernel")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="time eager launches instead of CUDA-graph replays (single-GPU runs replay graphs by default)")
+    ap.add_argument("--tile-schedule", default="dynamic", choices=["dynamic", "fixed"],
+                    help="tcgen05 kernel: tiles drawn from a device counter (default) or the fixed, bit-reproducible round-robin")
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (weak) or in total (strong); default 32 = the bench workload")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch images on every GPU; strong: --batch images in total, split over the GPUs")

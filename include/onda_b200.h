@@ -73,6 +73,11 @@ unsigned long long onda_launch_count(void);
 int onda_kernel_timing_enable(int enable);
 int onda_kernel_timing_read(float* total_ms_host, int* launches_host);
 
+/* Tile schedule of the tcgen05 kernel (process-wide; returns the previous value).  1 (default, or ONDA_TC_DYNAMIC_TILES
+ * unset): tiles beyond the first two per SM are drawn from a device counter -- fastest, but which SM accumulates which
+ * tile, and with it the last bits of the class sums, varies from run to run.  0: fixed round-robin schedule, class sums
+ * bit-reproducible (what a test that compares two runs bit for bit wants).  Other values only query. */
+int onda_set_tile_schedule(int dynamic);
 /* Diagnostics: when a device buffer of gridDim*32*8 int64 is set, the tcgen05 kernel records per-warp cycle
  * counters (time spent in each pipeline wait, total) into it.  NULL (default) disables it. */
 int onda_debug_set_buffer(void* device_buffer);

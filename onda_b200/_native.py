@@ -27,6 +27,7 @@ _SIGNATURES = {
     "onda_last_error": (C.c_char_p, []),
     "onda_sm_count": (C.c_int, []),
     "onda_launch_count": (C.c_ulonglong, []),
+    "onda_set_tile_schedule": (C.c_int, [C.c_int]),
     "onda_debug_set_buffer": (C.c_int, [_p]),
     "onda_debug_load_probe": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
     "onda_kernel_timing_enable": (C.c_int, [C.c_int]),

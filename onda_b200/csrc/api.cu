@@ -2,6 +2,7 @@
 // distance-table build, fixed-order partial reduction, EMA / cumulative prototype updates and
 // the prior-mix / switch-statistics kernel.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "epilogue.cuh"
@@ -24,6 +25,10 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 static unsigned long long g_launches = 0;
+// Tile schedule of the tcgen05 kernel: 1 = tiles drawn from a device counter (default; fastest), 0 = fixed round-robin
+// (class sums bit-reproducible from run to run).  ONDA_TC_DYNAMIC_TILES=0 in the environment changes the default.
+static int g_dynamic_tiles = [] { const char* e = getenv("ONDA_TC_DYNAMIC_TILES"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+bool tile_schedule_dynamic() { return g_dynamic_tiles != 0; }
 static long long* g_debug = nullptr;       // optional device buffer for cycle / time stamps (onda_debug_set_buffer)
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
@@ -687,6 +692,12 @@ int onda_sm_count(void) {
 }
 
 unsigned long long onda_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int onda_set_tile_schedule(int dynamic) {
+    const int prev = g_dynamic_tiles;
+    if (dynamic == 0 || dynamic == 1) g_dynamic_tiles = dynamic;
+    return prev;
+}
 
 int onda_debug_set_buffer(void* device_buffer) {
     g_debug = (long long*)device_buffer;

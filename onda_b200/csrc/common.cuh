@@ -13,6 +13,7 @@ namespace onda {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n);
+bool tile_schedule_dynamic();      // onda_set_tile_schedule / ONDA_TC_DYNAMIC_TILES
 // optional event bracket around the dominant kernel (api.cu); both are no-ops unless timing is enabled
 void timing_begin(cudaStream_t s);
 void timing_end(cudaStream_t s);

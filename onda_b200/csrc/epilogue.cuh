@@ -23,6 +23,7 @@ struct FusedParams {
     float* stat_partials;  // [n_stat_ctas][kStatSlots]
     float* dots_scratch;   // [nslices][CP + 1][N] partial dot products when nslices > 1
     unsigned* sched;       // tile counters of the tcgen05 kernel (inside the distance table, TableLayout::off_sched)
+    int dynamic_tiles;     // tcgen05 kernel: draw tiles from the counters (ONDA_TC_DYNAMIC_TILES=1) instead of the fixed round-robin
     int nslices;           // channel slices (gridDim.y)
     int slice_channels;    // channels per slice, multiple of 32
     int tiles;             // CUDA-core kernel: ceil(N / 128) tiles of the flattened pixel axis; tcgen05 kernel: B * tiles_per_img

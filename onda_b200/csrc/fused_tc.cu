@@ -51,6 +51,7 @@
 // Two accumulator buffers of 32 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <utility>
 
@@ -82,7 +83,7 @@ constexpr uint32_t kAccCol0 = kTcAStages * 64;   // accumulators after the A sta
 constexpr uint32_t kAccSet = 96;                 // per tile parity: three accumulators of 32 columns (one per term of the split, so
                                                  // that consecutive MMAs do not wait for each other's accumulator)
 constexpr uint32_t kApartCol0 = kAccCol0 + 2 * kAccSet;   // then sum_j w_j x'_j^2 of each chunk: 2 tile parities x 8 chunks, lane = pixel
-constexpr int kTcHeadFloats = kTcSumGroups * 2 * 3 * kTcChunkC;   // per statistic: head partials of ranges 1..3 of every group's current chunk, double-buffered over the group's chunks
+constexpr int kTcHeadFloats = kTcSumGroups * 2 * 3 * 2 * kTcChunkC;   // per statistic: head partials of ranges 1..3 of every group's current chunk pair, double-buffered over the group's pairs
 constexpr uint32_t kSpinLimit = 4000000u;        // failed probes (each up to ~1 us of hardware suspension) before giving up
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -159,6 +160,12 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v)); }
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -276,20 +283,22 @@ __host__ __device__ inline TcSmem tc_smem(int Dc, int C, int CP, bool sums, int 
     s.mu = o; o += (size_t)Dc * 4;
     s.w = o; o += (size_t)Dc * 4;
     s.btab = o; o += (size_t)2 * BR * Dc * 4;
-    s.acc = o; o += sums ? (size_t)2 * (C * Dc + kTcHeadFloats) * 4 : 0;   // [class * Dc/32 + chunk | then 3 heads per group][sum | sum of squares][32 channels]
+    s.acc = o; o += sums ? (size_t)2 * (C * Dc + kTcHeadFloats) * 4 : 0;   // blocks [class * Dc/64 + chunk pair | then 3 heads x 2 buffers per group] of [sum | sum of squares][32 lanes][chunk of the pair]
     o = (o + 127) / 128 * 128;
     s.ring = o; o += (size_t)nstage * kTcStageBytes;
     s.total = o;
     s.nstage = nstage;
     return s;
 }
-// as many ring stages as fit under the per-CTA limit (227 KB), at most kTcMaxStages; 0 = does not fit
+// as many ring stages as fit under the per-CTA limit (227 KB): an even number (the summers take the chunks in pairs
+// whose stages must be neighbours), at least 4, at most kTcMaxStages; 0 = does not fit
 __host__ inline int tc_ring_stages(int Dc, int C, int CP, bool sums) {
     const size_t fixed = tc_smem(Dc, C, CP, sums, 0).total;
     const size_t limit = 227 * 1024;
-    if (fixed + 3 * (size_t)kTcStageBytes > limit) return 0;
+    if (fixed + 4 * (size_t)kTcStageBytes > limit) return 0;
     size_t n = (limit - fixed) / kTcStageBytes;
-    return (int)(n > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : n);
+    n = n > (size_t)kTcMaxStages ? (size_t)kTcMaxStages : n;
+    return (int)(n & ~(size_t)1);
 }
 
 // the four tensor maps of the feature map (one per channel residue mod 4) and each map's shift
@@ -348,6 +357,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     if (SUMS) {
         for (int i = tid; i < 2 * (C * Dc + kTcHeadFloats); i += kTcThreads) acc[i] = 0.f;
         if (tid < 32) cnt[tid] = 0;
+        if (tid < 16) cuts[16 + tid] = 0;       // landed[] of the summers' watchers
     }
     if (tid == 0) {
         {   // B operand table of this CTA's channel slice: one bulk asynchronous copy, issued first and off everybody's
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             mbar_init(acc_full(i), 1);
             mbar_init(acc_empty(i), 128);
             mbar_init(sort_ready(i), 64);
-            mbar_init(sort_free(i), 4 * (NB < kTcSumGroups ? NB : kTcSumGroups));   // the summer warps that have chunks
+            mbar_init(sort_free(i), 4 * (NB / 2 < kTcSumGroups ? NB / 2 : kTcSumGroups));   // the summer warps that have chunk pairs
         }
         for (int i = 0; i < kTcTileQ; ++i) mbar_init(tq_full(i), 1);
         fence_barrier_init();
@@ -389,9 +399,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     const long long t_start = PROF ? clock64() : 0;
     const unsigned tpi = (unsigned)p.tiles_per_img;
     const unsigned HWu = (unsigned)HW;
-    // Tiles are handed out dynamically (the producer draws them from a global counter two steps ahead and publishes
-    // them in the queue): SMs do not run at the same speed, and tiles / SMs is rarely an integer.  The tile of this
-    // CTA's t-th step, or -1 when there is none:
+    // The producer publishes the CTA's tile schedule in a small queue (fixed round-robin by default, optionally drawn
+    // from a global counter).  The tile of this CTA's t-th step, or -1 when there is none:
     auto tile_at = [&](int t) -> int {
         mbar_wait(tq_full(t & (kTcTileQ - 1)), ((uint32_t)t / kTcTileQ) & 1);
         return tq[t & (kTcTileQ - 1)];
@@ -482,136 +491,163 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         // =========================== summers ===========================================
         reg_dec<kTcRegsSum>();
         if (SUMS) {
-        // Class sums of the chunk's 32 channels (lane = channel), read straight from the ring stage.  The class-sorted
-        // pixels of the tile are cut into four ranges of 32 entries, one per warp of the group: balanced whatever the
-        // label map looks like.  The pixel offsets of the entries come four at a time from warp-uniform (broadcast)
-        // 16-byte loads, sixteen feature loads are in flight at once, and the segment ends are a warp-uniform bit mask:
-        // an end adds the running (sum, sum of squares) to the segment's accumulator row.  A range that
-        // starts inside a class accumulates that first segment (its "head") into a spare row -- same code, the sorter
-        // just marks those entries -- which the warp that started the class adds to the class row after the group's
-        // barrier, heads in range order.  One writer per accumulator at a time, fixed order, no atomics.
+        // Class sums of a PAIR of chunks (2 x 32 channels; lane = channel of either chunk), read straight from the two
+        // ring stages: the pair shares the walk over the sorted list -- offsets, address arithmetic, segment tests -- and
+        // its two values per entry go through the packed f32x2 pipe together.  The class-sorted pixels of the tile are
+        // cut into four ranges of 32 entries, one per warp of the group: balanced whatever the label map looks like.
+        // The pixel offsets of the entries come four at a time from warp-uniform (broadcast) 16-byte loads, sixteen
+        // feature loads are in flight at once, and the segment ends are a warp-uniform bit mask: an end adds the
+        // running (sum, sum of squares) to the segment's accumulator block.  A range that starts inside a class
+        // accumulates that first segment (its "head") into a spare block -- same code, the sorter just marks those
+        // entries -- which the warp that started the class adds to the class block after the group's barrier, heads
+        // in range order.  One writer per accumulator at a time, fixed order, no atomics.
+        // Accumulator block of (class, pair): [sum | sum of squares][32 lanes][chunk 0 | chunk 1] = 512 bytes.
         const int sw = warp - kTcSumWarp0;
-        const int quarter = sw & 3, group = sw >> 2;        // quarter = which 32 sorted entries; group g takes chunks g, g+4, .. of a tile
+        const int quarter = sw & 3, group = sw >> 2;        // quarter = which 32 sorted entries; group g takes pairs g, g+4, .. of a tile
         const int gbar = 3 + group;                         // named barrier of the group (128 threads)
-        int stage = 0, qprev = 0;
-        uint32_t rphase = 0;
-        int hp = 0;                                         // head buffer of this chunk (alternates over the group's chunks)
+        const int NP = NB >> 1;                             // chunk pairs per tile (NB is even)
+        int stage = 0, qprev = 0;                           // ring stage of the pair's first chunk: even (the ring has an even number of stages)
+        int hp = 0;                                         // head buffer of this pair (alternates over the group's pairs)
+        int use = 0;                                        // how many times that stage has been filled before (phase = use & 1)
+        volatile int* landed = cuts + 16;                   // per stage: fills seen complete by their consumers' watchers
         const uint32_t lane_off = (uint32_t)ring_slot(lane) * kTcRowBytes + 4u * (uint32_t)maps.shift[lane & 3];   // pixel 0 of this lane's channel row
         const int idx = 32 * quarter + lane;                // this warp's range: entries 32*quarter .. +31
-        const bool single = group + kTcSumGroups >= NB;     // one chunk per tile: consecutive chunks of the group share their accumulator rows
+        const bool single = group + kTcSumGroups >= NP;     // one pair per tile: consecutive pairs of the group share their accumulator blocks
         for (int t = 0; tile_at(t) >= 0; ++t)
-        for (int blk = group; blk < NB; blk += kTcSumGroups, hp ^= 1) {
-            {   // ring stage of chunk q = t * NB + blk
-                const int q = t * NB + blk;
+        for (int pr = group; pr < NP; pr += kTcSumGroups, hp ^= 1) {
+            {   // ring stage of chunk q = t * NB + 2 * pr
+                const int q = t * NB + 2 * pr;
                 stage += q - qprev;
                 qprev = q;
-                while (stage >= nstage) { stage -= nstage; rphase ^= 1; }
+                while (stage >= nstage) { stage -= nstage; ++use; }
             }
             const int par = t & 1;
             if (quarter == 0) {              // one warp of the group watches the mbarriers, the others sleep in the barrier
                 mbar_wait_t(sort_ready(par), ((uint32_t)t >> 1) & 1, prof, dbg[1]);
-                mbar_wait_t(ring_full(stage), rphase, prof, dbg[0]);
+                // A parity wait is only sound on a barrier that is at most one phase away, and this group consumes only
+                // some of the fills of a stage (the others belong to other groups).  So every watcher publishes the
+                // fills it has seen complete (landed[stage] = fills so far), and a watcher first makes sure the fill
+                // before its own has been seen -- which never waits longer than the data itself: its own fill cannot
+                // even be requested before that one's consumers have released the stage.
+                if (use > 0) {
+                    long long spins = 0;
+                    while (landed[stage] < use || landed[stage + 1] < use) {
+                        __nanosleep(64);
+                        if (++spins > kSpinLimit) __trap();
+                    }
+                }
+                mbar_wait_t(ring_full(stage), (uint32_t)use & 1u, prof, dbg[0]);
+                mbar_wait_t(ring_full(stage + 1), (uint32_t)use & 1u, prof, dbg[0]);
+                if (lane == 0) {
+                    landed[stage] = use + 1;
+                    landed[stage + 1] = use + 1;
+                }
             }
             named_bar_sync(gbar, 128);
             const long long t_seg0 = prof ? clock64() : 0;
-            const uint32_t row_lane = ring + (uint32_t)stage * kTcStageBytes + lane_off;
+            const uint32_t row_lane = ring + (uint32_t)stage * kTcStageBytes + lane_off;     // second chunk: + kTcStageBytes
             const uint32_t eo = smem_u32(eoff + par * kTilePixels + 32 * quarter);     // byte offsets of this range's 32 pixels in a row
             const int* ct = cuts + par * 8;
-            // accumulators: row (class * NB + blk), then [sum | sum of squares][32 channels]: the pair of a flush is 128 bytes apart
-            const uint32_t a1 = smem_u32(acc) + (uint32_t)(blk * 64 + lane) * 4u;     // + row offset of the class (bytes, from the sorter)
-            const uint32_t head_base = (uint32_t)(C * NB + (group * 2 + hp) * 3 - blk) * 256u;   // head j of this group's chunk, relative to a1: + (j-1)*256
+            const uint32_t a1 = smem_u32(acc) + (uint32_t)(pr * 512 + lane * 8);      // + block offset of the class (bytes, from the sorter)
+            const uint32_t head_base = (uint32_t)(C * NP + (group * 2 + hp) * 3 - pr) * 512u;   // head j of this group's pair, relative to a1: + (j-1)*512
             int nlive = ct[0] - 32 * quarter;                                         // ct[0] = live entries of the tile
             nlive = nlive < 0 ? 0 : (nlive > 32 ? 32 : nlive);
-            const int er_i = ecls[par * kTilePixels + idx];                           // bit 0: segment end, bit 1: head segment, else class row offset
+            const int er_i = ecls[par * kTilePixels + idx];                           // bit 0: segment end, bit 1: head segment, else class block offset
             const unsigned endbits = __ballot_sync(0xffffffffu, er_i & 1);            // segment ends (sorter: class end or entry 31)
-            const uint32_t myrow = (er_i & 2) ? head_base + (uint32_t)(quarter - 1) * 256u : (uint32_t)(er_i & ~3);   // accumulator row (bytes) of this entry's segment
-            // The accumulator pair of the running segment is fetched when the segment starts, so a flush is an add and
-            // two stores; entries past the last live one need no guard: that one ends a segment, so whatever they add
-            // to the running pair is never flushed (their rows are the zero-filled padding of the tile anyway).
+            const uint32_t myrow = (er_i & 2) ? head_base + (uint32_t)(quarter - 1) * 512u : (uint32_t)(er_i & ~3);   // accumulator block (bytes) of this entry's segment
+            // The accumulators of the running segment are fetched when the segment starts, so a flush is two packed adds
+            // and two stores; entries past the last live one need no guard: that one ends a segment, so whatever they add
+            // to the running sums is never flushed (their rows are the zero-filled padding of the tile anyway).
             uint32_t cur = a1 + (uint32_t)__shfl_sync(0xffffffffu, myrow, 0);
-            float c1 = lds32(cur), c2 = lds32(cur + 128u);
-            float s1 = 0.f, s2 = 0.f;
+            uint64_t c1 = lds64(cur), c2 = lds64(cur + 256u);
+            uint64_t s1 = 0ull, s2 = 0ull;            // (chunk 0, chunk 1) running sum / sum of squares
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {            // 16 entries at a time: all their loads in flight at once (kept rolled: code size)
-                if (16 * h >= nlive) continue;
-                int4 ov[4];
+            for (int h = 0; h < 4; ++h) {            // 8 entries x 2 chunks at a time: sixteen loads in flight (kept rolled: code size)
+                if (8 * h >= nlive) break;
+                int4 ov[2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)          // warp-uniform address: one broadcast 16-byte load gives four offsets
-                    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(ov[i].x), "=r"(ov[i].y), "=r"(ov[i].z), "=r"(ov[i].w) : "r"(eo + 64u * h + 16u * i));
-                float xv[16];
+                for (int i = 0; i < 2; ++i)          // warp-uniform address: one broadcast 16-byte load gives four offsets
+                    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(ov[i].x), "=r"(ov[i].y), "=r"(ov[i].z), "=r"(ov[i].w) : "r"(eo + 32u * h + 16u * i));
+                uint64_t xv[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    xv[4 * i + 0] = lds32(row_lane + (uint32_t)ov[i].x);
-                    xv[4 * i + 1] = lds32(row_lane + (uint32_t)ov[i].y);
-                    xv[4 * i + 2] = lds32(row_lane + (uint32_t)ov[i].z);
-                    xv[4 * i + 3] = lds32(row_lane + (uint32_t)ov[i].w);
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t o0 = row_lane + (uint32_t)ov[i].x, o1 = row_lane + (uint32_t)ov[i].y;
+                    const uint32_t o2 = row_lane + (uint32_t)ov[i].z, o3 = row_lane + (uint32_t)ov[i].w;
+                    xv[4 * i + 0] = pack2(lds32(o0), lds32(o0 + (uint32_t)kTcStageBytes));
+                    xv[4 * i + 1] = pack2(lds32(o1), lds32(o1 + (uint32_t)kTcStageBytes));
+                    xv[4 * i + 2] = pack2(lds32(o2), lds32(o2 + (uint32_t)kTcStageBytes));
+                    xv[4 * i + 3] = pack2(lds32(o3), lds32(o3 + (uint32_t)kTcStageBytes));
                 }
-                if (h == 1 || nlive <= 16) {         // the stage's last reads are issued: release it (ordered before the arrive)
+                if (h == 3 || nlive <= 8 * h + 8) {  // the stages' last reads are issued: release them (ordered before the arrives)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(ring_empty(stage));
+                    if (lane == 0) {
+                        mbar_arrive(ring_empty(stage));
+                        mbar_arrive(ring_empty(stage + 1));
+                    }
                 }
                 // four entries at a time: without a segment end among the first three, the quad is a small tree (short
                 // dependent chains, one test); otherwise entry by entry.  Either way the order of the additions is a
                 // function of the sorted list alone.
-                const unsigned hb = endbits >> (16 * h);
-                auto flush = [&](int e) {            // entry e (0..15 of this half) ends a segment
-                    sts32(cur, c1 + s1);
-                    sts32(cur + 128u, c2 + s2);
-                    s1 = 0.f;
-                    s2 = 0.f;
-                    if (16 * h + e < 31) {           // the next segment's accumulators
-                        cur = a1 + (uint32_t)__shfl_sync(0xffffffffu, myrow, 16 * h + e + 1);
-                        c1 = lds32(cur);
-                        c2 = lds32(cur + 128u);
+                const unsigned hb = endbits >> (8 * h);
+                auto flush = [&](int e) {            // entry e (0..7 of this step) ends a segment
+                    sts64(cur, fadd2(c1, s1));
+                    sts64(cur + 256u, fadd2(c2, s2));
+                    s1 = 0ull;
+                    s2 = 0ull;
+                    if (8 * h + e < 31) {            // the next segment's accumulators
+                        cur = a1 + (uint32_t)__shfl_sync(0xffffffffu, myrow, 8 * h + e + 1);
+                        c1 = lds64(cur);
+                        c2 = lds64(cur + 256u);
                     }
                 };
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const float x0 = xv[4 * qd], x1 = xv[4 * qd + 1], x2 = xv[4 * qd + 2], x3 = xv[4 * qd + 3];
+                for (int qd = 0; qd < 2; ++qd) {
+                    const uint64_t x0 = xv[4 * qd], x1 = xv[4 * qd + 1], x2 = xv[4 * qd + 2], x3 = xv[4 * qd + 3];
                     const unsigned qb = (hb >> (4 * qd)) & 0xfu;
                     if ((qb & 7u) == 0u) {
-                        const uint64_t p01 = pack2(x0, x1), p23 = pack2(x2, x3);
-                        const uint64_t t1 = fadd2(p01, p23), t2 = ffma2(p23, p23, fmul2(p01, p01));
-                        s1 += __uint_as_float((uint32_t)t1) + __uint_as_float((uint32_t)(t1 >> 32));
-                        s2 += __uint_as_float((uint32_t)t2) + __uint_as_float((uint32_t)(t2 >> 32));
+                        s1 = fadd2(s1, fadd2(fadd2(x0, x1), fadd2(x2, x3)));
+                        s2 = fadd2(s2, fadd2(ffma2(x1, x1, fmul2(x0, x0)), ffma2(x3, x3, fmul2(x2, x2))));
                         if (qb & 8u) flush(4 * qd + 3);
                     } else {
-                        s1 += x0; s2 = fmaf(x0, x0, s2);
+                        s1 = fadd2(s1, x0); s2 = ffma2(x0, x0, s2);
                         if (qb & 1u) flush(4 * qd);
-                        s1 += x1; s2 = fmaf(x1, x1, s2);
+                        s1 = fadd2(s1, x1); s2 = ffma2(x1, x1, s2);
                         if (qb & 2u) flush(4 * qd + 1);
-                        s1 += x2; s2 = fmaf(x2, x2, s2);
+                        s1 = fadd2(s1, x2); s2 = ffma2(x2, x2, s2);
                         if (qb & 4u) flush(4 * qd + 2);
-                        s1 += x3; s2 = fmaf(x3, x3, s2);
+                        s1 = fadd2(s1, x3); s2 = ffma2(x3, x3, s2);
                         if (qb & 8u) flush(4 * qd + 3);
                     }
                 }
             }
             if (nlive == 0) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(ring_empty(stage));
+                if (lane == 0) {
+                    mbar_arrive(ring_empty(stage));
+                    mbar_arrive(ring_empty(stage + 1));
+                }
             }
             if (prof) dbg[3] += clock64() - t_seg0;
-            named_bar_sync(gbar, 128);          // all heads of this chunk are complete
-            {   // move the heads of the classes this warp started into their class rows
+            named_bar_sync(gbar, 128);          // all heads of this pair are complete
+            {   // move the heads of the classes this warp started into their class blocks
                 const int hj = (lane >= 1 && lane < 4) ? ct[lane] : -1;
                 unsigned m = __ballot_sync(0xffffffffu, hj >= 0 && (hj >> 8) == quarter);
                 while (m) {
                     const int j = __ffs(m) - 1;
                     m &= m - 1;
                     const int k = __shfl_sync(0xffffffffu, hj, j) & 0xff;
-                    const uint32_t hd = a1 + head_base + (uint32_t)(j - 1) * 256u, ad = a1 + (uint32_t)(k * NB) * 256u;
-                    sts32(ad, lds32(ad) + lds32(hd));
-                    sts32(ad + 128u, lds32(ad + 128u) + lds32(hd + 128u));
-                    sts32(hd, 0.f);
-                    sts32(hd + 128u, 0.f);
+                    const uint32_t hd = a1 + head_base + (uint32_t)(j - 1) * 512u, ad = a1 + (uint32_t)(k * NP) * 512u;
+                    sts64(ad, fadd2(lds64(ad), lds64(hd)));
+                    sts64(ad + 256u, fadd2(lds64(ad + 256u), lds64(hd + 256u)));
+                    sts64(hd, 0ull);
+                    sts64(hd + 256u, 0ull);
                 }
             }
-            // The head rows alternate between two buffers, so the next chunk's heads cannot meet this chunk's moves; the
-            // class rows of a chunk are revisited two chunks later, behind one more group barrier -- except when the
-            // group owns a single chunk per tile: then the next chunk flushes into the very same rows.
+            // The head blocks alternate between two buffers, so the next pair's heads cannot meet this pair's moves; the
+            // class blocks of a pair are revisited two pairs later, behind one more group barrier -- except when the
+            // group owns a single pair per tile: then the next pair flushes into the very same blocks.
             if (single) named_bar_sync(gbar, 128);
-            if (blk + kTcSumGroups >= NB) {     // that was this group's last chunk of the tile
+            if (pr + kTcSumGroups >= NP) {      // that was this group's last pair of the tile
                 if (lane == 0) mbar_arrive(sort_free(par));
             }
         }
@@ -753,12 +789,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             for (int r = 0; r < 4; ++r) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.map[r]) : "memory");
             int stage = 0;
             uint32_t rphase = 0;
-            // Tile schedule: steps 0 and 1 are static (tiles blockIdx.x and blockIdx.x + gridDim.x), later ones are drawn
-            // from this slice's counter while the copies of two steps earlier are being issued, and published one step
-            // before anybody needs them (the sorter reads one step ahead).
+            // Tile schedule, published through the queue one step before anybody needs it (the sorter reads one step
+            // ahead).  Default: the first two tiles are fixed (blockIdx.x, blockIdx.x + gridDim.x), later ones are drawn
+            // from this slice's counter while the copies of two steps earlier are being issued -- SMs do not run at
+            // the same speed and tiles / SMs is rarely an integer: 4-5 % faster at 14.3 tiles per SM.  Which CTA
+            // accumulates which tile then varies from run to run, and with it the last bits of the class sums (labels,
+            // soft predictions and statistics of the step do not depend on them).  onda_set_tile_schedule(0): the
+            // fixed round-robin tile blockIdx.x + t * gridDim.x, bit-reproducible.
             const int G = (int)gridDim.x;
             unsigned* counter = p.sched + blockIdx.y;
-            const bool drawing = p.tiles > 2 * G;          // else every tile is one of the static two per CTA
+            const bool drawing = p.dynamic_tiles != 0 && p.tiles > 2 * G;      // else: tile blockIdx.x + t * gridDim.x, as a fixed schedule
             int cur = (int)blockIdx.x, nxt = (int)blockIdx.x + G < p.tiles ? (int)blockIdx.x + G : -1;
             tq[0] = cur;
             tq[1] = nxt;
@@ -766,7 +806,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             mbar_arrive(tq_full(1));
             for (int t = 0; cur >= 0; ++t) {
                 int after = -1;
-                if (nxt >= 0 && drawing) after = 2 * G + (int)atomicAdd(counter, 1u);
+                if (nxt >= 0) after = drawing ? 2 * G + (int)atomicAdd(counter, 1u) : nxt + G;
                 unsigned img, pix0;
                 int npx;
                 tile_of(cur, img, pix0, npx);
@@ -901,12 +941,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     const long long t_sync_end = PROF ? clock64() : 0;
     if (SUMS) {
         float* out = p.cta_partials + (size_t)blockIdx.x * sums_floats(C, D);
-        // accumulator row r = (class * NB + chunk) * 2 + statistic, 32 channels -> out: [sum | sum of squares][class][D]
-        const unsigned inv_nb = (65536u + (unsigned)NB - 1u) / (unsigned)NB;      // kc / NB = (kc * inv_nb) >> 16 for kc < 2^13
-        for (int r = warp; r < 2 * C * NB; r += kTcThreads / 32) {
+        // accumulator row r = (class * NP + pair) * 2 + statistic: 32 lanes x (chunk 2 pair | chunk 2 pair + 1)
+        // -> out: [sum | sum of squares][class][D]
+        const int NP = NB >> 1;
+        const unsigned inv_np = (65536u + (unsigned)NP - 1u) / (unsigned)NP;      // kc / NP = (kc * inv_np) >> 16 for kc < 2^13
+        for (int r = warp; r < 2 * C * NP; r += kTcThreads / 32) {
             const int stat = r & 1, kc = r >> 1;
-            const int k = (int)(((unsigned)kc * inv_nb) >> 16), chunk = kc - k * NB;
-            out[(size_t)(stat * C + k) * D + c_base + chunk * 32 + lane] = acc[r * 32 + lane];
+            const int k = (int)(((unsigned)kc * inv_np) >> 16), pr = kc - k * NP;
+            const float2 v = reinterpret_cast<const float2*>(acc)[r * 32 + lane];
+            float* dst = out + (size_t)(stat * C + k) * D + c_base + pr * 64 + lane;
+            dst[0] = v.x;
+            dst[32] = v.y;
         }
         if (tid < C && blockIdx.y == 0) out[(size_t)2 * C * D + tid] = (float)cnt[tid];
     }
@@ -939,7 +984,7 @@ bool tc_supported(int B, int D, int HW, int C) {
     (void)B; (void)HW;
     const int dc = tc_slice_channels(D);
     if (dc == 0 || D / dc > 16 || C < 1 || C > 32) return false;
-    return tc_ring_stages(dc, C, padded_classes(C), true) >= 3;
+    return tc_ring_stages(dc, C, padded_classes(C), true) >= 4;
 }
 
 int tc_tiles(int B, int HW) { return B * ((HW + kTilePixels - 1) / kTilePixels); }
@@ -1017,6 +1062,7 @@ static int launch_tc(FusedParams p, int grid, cudaStream_t stream) {
         ONDA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set[dev] = smem;
     }
+    p.dynamic_tiles = tile_schedule_dynamic() ? 1 : 0;
     TcMaps maps;
     const int rc = tc_make_maps(p.feat, p.B, p.D, p.HW, &maps);
     if (rc != ONDA_OK) return rc;

@@ -61,7 +61,7 @@ class prototype_handler:
 
     def __init__(self, ma_lambda=0.9999, tau=1, thresh=0, distance_metric="euclidean",
                  confidence_regularization_threshold=1, impl="auto", process_group=None, fuse_hard_soft=True,
-                 allreduce="nccl"):
+                 allreduce="nccl", tile_schedule="dynamic"):
         self.prototypes = 0  # classes x features once appended / loaded (prototype_handler.py:17)
         self.squared_mean = 0
         self.counter = 0
@@ -89,6 +89,12 @@ class prototype_handler:
         self.allreduce = allreduce     # "nccl": torch.distributed all_reduce; "oneshot": own NVLink peer-memory kernel
         self._symm = None              # (tensor, handle, n, slot_floats) of the one-shot all-reduce
         self._ar_calls = 0
+        if tile_schedule not in ("dynamic", "fixed"):
+            raise ValueError(f"unknown tile_schedule {tile_schedule!r}")
+        # tcgen05 kernel: "dynamic" draws the tiles of an SM from a device counter (fastest; which SM accumulates which
+        # tile, and so the last bits of the class sums, vary from run to run); "fixed" is the round-robin schedule
+        # whose class sums are bit-reproducible.
+        self.tile_schedule = tile_schedule
         self.fuse_hard_soft = fuse_hard_soft
         self._stats_src = None     # (sums, C, D) of the last fused pass
         self._local_stats = None   # same, never replaced by the all-reduced buffer
@@ -232,6 +238,7 @@ class prototype_handler:
         with _on(device):
             wbytes = self._lib.onda_fused_workspace_bytes(B, D, HW, C, impl)
             work = self._buf("work", (wbytes,), torch.uint8, device)
+            self._lib.onda_set_tile_schedule(1 if self.tile_schedule == "dynamic" else 0)
             nat.check(self._lib.onda_pseudolabel_fused_guarded(
                 nat.ptr(feat3), nat.ptr(prior3), nat.ptr(logits3), nat.ptr(table), B, D, HW, C,
                 float(self.tau), float(self.thresh), nat.ptr(labels), nat.ptr(soft), nat.ptr(dist), nat.ptr(sums),

@@ -437,6 +437,27 @@ def test_full_size_oracle_parity(seed, B, D, h, w, impl):
     assert st["entropy"] == pytest.approx(ref_entropy, abs=2e-6)
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("B,D", [(32, 256), (4, 2048)])
+def test_step_is_bit_reproducible(B, D, impl):
+    """Many tiles per SM, several launches, tile_schedule="fixed": labels, soft predictions and the post-ma state are
+    the same bits every time (one writer per accumulator, fixed-order combine: north_star's deterministic class sums).
+    The default dynamic schedule gives up exactly this (the last bits of the class sums) for 4-5 % of the kernel time."""
+    need_shape(impl, D)
+    case = po.synth_case(77, B, D, 65, 129)
+    feat, prior, out = (case[k].to(dev()) for k in ("feat", "prior", "out"))
+    runs = []
+    for _ in range(4):
+        hd = make_handler(case["protos"], case["sq_mean"], case["counter"], "mahalanobis", impl=impl)
+        hd.tile_schedule = "fixed"
+        labels, soft = hd.pseudo_labels_fused(feat, prior, out)
+        hd.ma(feat, out)
+        runs.append((labels.clone(), soft.clone(), hd.prototypes.clone(), hd.squared_mean.clone()))
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b)
+
+
 # --------------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties
 # --------------------------------------------------------------------------------------

@@ -95,7 +95,7 @@ def _graph_worker(rank, world, port, n_graphs, ret):
         results = []
         for use_graph in (False, True):
             h = prototype_handler(ma_lambda=0.9, tau=1, thresh=0.3, distance_metric="mahalanobis",
-                                  process_group=dist.group.WORLD, allreduce="oneshot")
+                                  process_group=dist.group.WORLD, allreduce="oneshot", tile_schedule="fixed")   # bit-for-bit comparison below
             h.prototypes, h.squared_mean, h.counter = (case[k].clone().to(dev) for k in ("protos", "sq_mean", "counter"))
 
             def step(k):
