@@ -16,28 +16,30 @@
 // 8 channels (box 132 x 8 x 1, 4 extra floats of padding per row, out-of-range elements zero-filled) and four of
 // them fetch a 32-channel chunk into a ring stage: rows grouped by residue, slot 8*r + a, 528-byte pitch, the row
 // of residue r starting shift_r floats into its slot (boxes start at float index pix0: 16-byte aligned addresses).  No thread issues a global load for the features, no registers
-// hold loads in flight, and the memory-level parallelism is the ring depth (5-6 stages of 16.5 KB), not the warp
+// hold loads in flight, and the memory-level parallelism is the ring depth (6 stages of 16.5 KB), not the warp
 // count.  A tile is 128 consecutive pixels of ONE image (the last tile of an image is partial).
 //
-// One persistent CTA per SM, 32 warps, over a single global chunk sequence (chunk = 128 pixels x 32 channels;
-// a tile is D/32 consecutive chunks; chunk q uses ring stage q % nstage and TMEM A stage q % 4):
-//   warp   31    producer: one thread; waits for the ring stage to be free, then issues the chunk's four tensor
-//                copies (mbarrier expect_tx / complete_tx).
+// One persistent CTA per SM, 32 warps, over a single chunk sequence (chunk = 128 pixels x 32 channels; a tile is D/32
+// consecutive chunks; chunk q uses ring stage q % nstage -- nstage is even -- and TMEM A stage q % 4):
+//   warp   31    producer: one thread; publishes the CTA's tile schedule in a small shared-memory queue (fixed
+//                round-robin, or drawn from a global counter two steps ahead: onda_set_tile_schedule), waits for the
+//                ring stage to be free, then issues the chunk's four tensor copies (mbarrier expect_tx / complete_tx).
 //   warps  0-7   converters, two groups of four; warp w%4 is the pixel quarter (the only TMEM lanes a warp may
 //                touch are 32*(w%4)..+31), group g takes chunks g, g+2, ...  Per chunk: lane = pixel reads the
 //                32 channel rows of the stage (consecutive lanes = consecutive words: conflict-free), releases
 //                the stage, centres, accumulates sum_j w_j x'_j^2, splits into TF32 hi/lo with packed f32x2 math
 //                and writes both with tcgen05.st into TMEM as the A operand (lane = pixel, column = channel).
-//   warps  8-23  summers, four groups of four; group g takes the chunks g, g+4, .. of every tile: the class sums of
-//                the chunk straight from the ring stage, lane = channel.  With slot 8*(c%4) + c/4, 528-byte pitch and
-//                the row of residue c%4 starting shift(c%4) floats into its slot, the 32 lanes of a "same pixel, 32
-//                channels" read hit 32 different banks when H*W is odd (bank = 4*(c/4) + shift(c%4) + pixel; the four
-//                shifts are then distinct; an even H*W costs bank conflicts here, nothing else).  Each warp walks
-//                32 entries of the class-sorted pixel list and adds every segment's (sum, sum of squares) to that
-//                class's shared-memory accumulators; a range that starts inside a class parks that first segment
-//                in a spare row which the warp that started the class adds after the group's barrier.  One
+//   warps  8-23  summers, four groups of four; group g takes the chunk PAIRS g, g+4, .. of every tile: the class sums
+//                of both chunks straight from their two (neighbouring) ring stages, lane = channel of either chunk, the
+//                two values of an entry travelling through the packed f32x2 pipe together.  With slot 8*(c%4) + c/4,
+//                528-byte pitch and the row of residue c%4 starting shift(c%4) floats into its slot, the 32 lanes of a
+//                "same pixel, 32 channels" read hit 32 different banks when H*W is odd (bank = 4*(c/4) + shift(c%4) +
+//                pixel; the four shifts are then distinct; an even H*W costs bank conflicts here, nothing else).  Each
+//                warp walks 32 entries of the class-sorted pixel list and adds every segment's (sum, sum of squares) to
+//                that class's shared-memory accumulators; a range that starts inside a class parks that first segment
+//                in a spare block which the warp that started the class adds after the group's barrier.  One
 //                writer per accumulator at a time, fixed summation order, no atomics.
-//   warps 24-27  epilogue: tcgen05.ld of the 32 accumulator columns and the partial columns of their pixel,
+//   warps 24-27  epilogue: tcgen05.ld of the accumulator columns and the partial columns of their pixel,
 //                then the common per-pixel tail (epilogue.cuh): sqrt, softmax, prior rectification, label,
 //                statistics.
 //   warps 28-29  sorter: per tile, class of every pixel (first argmax of the EMA logits) and a stable
@@ -47,8 +49,11 @@
 //                is bound by reading A, so the two hi terms share one read), B = TF32 split of -2*w*(P-mu) resident
 //                in shared memory (one bulk copy in the prologue that only this warp waits for).
 // The register file is re-split after the prologue (setmaxnreg): converters 72, summers 56, epilogue 80, the rest 64.
-// Every mbarrier has one producer side and one consumer side that visit it phase by phase, in order.
-// Two accumulator buffers of 32 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
+// Inside a group of warps ONE warp watches the mbarriers (try_wait) and the others sleep in the group's named barrier.
+// A parity wait is only sound on a barrier the waiter is at most one phase away from: every mbarrier here has one
+// producer side and consumers that visit it phase by phase -- except the ring's "full" barriers, of whose fills a
+// summer group consumes only some: there the watchers publish fill counts and check them first (see the summers).
+// Two accumulator buffers of 96 TMEM columns; tcgen05.commit frees A stages / publishes accumulators.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -431,8 +436,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             const int par = t & 1;
             const int as = q & (kTcAStages - 1);
             const uint32_t use = (uint32_t)q >> 2;
-            if (quarter == 0) mbar_wait_t(ring_full(stage), rphase, prof, dbg[0]);      // one warp of the group watches the
-            named_bar_sync(cbar, 128);                                                       // mbarrier, the others sleep in the barrier
+            if (quarter == 0) {              // one warp of the group watches the mbarriers, the others sleep in the barrier
+                mbar_wait_t(ring_full(stage), rphase, prof, dbg[0]);
+                // ... including the two the conversion needs (practically always complete by now: the MMAs of four chunks
+                // ago, the epilogue of two tiles ago), so the group meets once per chunk
+                if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[1]);   // partial columns [par] of tile t-2 consumed
+                mbar_wait_t(empty_a(as), (use & 1) ^ 1, prof, dbg[2]);
+            }
+            named_bar_sync(cbar, 128);
+            tc_fence_after();
             {   // the 32 channel rows of this lane's pixel: row j sits in slot 8*(j%4) + j/4 and starts shift[j%4] floats in
                 const uint32_t sbase = ring + (uint32_t)stage * kTcStageBytes + lane_word;
 #pragma unroll
@@ -442,12 +454,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             if (lane == 0) mbar_arrive(ring_empty(stage));      // this warp's reads of the stage are issued and ordered before the arrive
             stage += kTcConvGroups;
             if (stage >= nstage) { stage -= nstage; rphase ^= 1; }
-            if (quarter == 0) {
-                if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[1]);   // partial columns [par] of tile t-2 consumed
-                mbar_wait_t(empty_a(as), (use & 1) ^ 1, prof, dbg[2]);
-            }
-            named_bar_sync(cbar, 128);
-            tc_fence_after();
             const long long t_cv0 = prof ? clock64() : 0;
             uint64_t a2 = 0;                       // sum_j w_j x'_j^2 of the even / odd channels (packed f32x2 math)
             const uint32_t tcol = tmem_base + lane_base + (uint32_t)as * 64;
@@ -512,7 +518,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
         volatile int* landed = cuts + 16;                   // per stage: fills seen complete by their consumers' watchers
         const uint32_t lane_off = (uint32_t)ring_slot(lane) * kTcRowBytes + 4u * (uint32_t)maps.shift[lane & 3];   // pixel 0 of this lane's channel row
         const int idx = 32 * quarter + lane;                // this warp's range: entries 32*quarter .. +31
-        const bool single = group + kTcSumGroups >= NP;     // one pair per tile: consecutive pairs of the group share their accumulator blocks
         for (int t = 0; tile_at(t) >= 0; ++t)
         for (int pr = group; pr < NP; pr += kTcSumGroups, hp ^= 1) {
             {   // ring stage of chunk q = t * NB + 2 * pr
@@ -643,10 +648,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                     sts64(hd + 256u, 0ull);
                 }
             }
-            // The head blocks alternate between two buffers, so the next pair's heads cannot meet this pair's moves; the
-            // class blocks of a pair are revisited two pairs later, behind one more group barrier -- except when the
-            // group owns a single pair per tile: then the next pair flushes into the very same blocks.
-            if (single) named_bar_sync(gbar, 128);
+            // The next pair's segment flushes (possibly into the very same class blocks) and head blocks (the other
+            // buffer) start behind the group barrier that opens that pair: every warp has finished its moves by then.
             if (pr + kTcSumGroups >= NP) {      // that was this group's last pair of the tile
                 if (lane == 0) mbar_arrive(sort_free(par));
             }
