@@ -121,6 +121,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try(bar, parity))
         if (++tries > kSpinLimit) __trap();
 }
+// Wait of a role with slack (MMA issuer, producer, sorter): plain probes a fixed time apart.  A suspended try_wait is
+// woken by mbarrier traffic and every wake-up is a handful of instructions in issue slots the working warps need;
+// these roles can afford up to `ns` of extra latency per wait instead.
+__device__ __forceinline__ void mbar_wait_slack(uint32_t bar, uint32_t parity, unsigned ns) {
+    uint32_t tries = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        __nanosleep(ns);
+        if (++tries > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_slack_t(uint32_t bar, uint32_t parity, unsigned ns, bool prof, long long& acc_cycles) {
+    if (!prof) { mbar_wait_slack(bar, parity, ns); return; }
+    const long long t0 = clock64();
+    mbar_wait_slack(bar, parity, ns);
+    acc_cycles += clock64() - t0;
+}
 // wait that adds its duration to a diagnostic counter when profiling is on
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, long long& acc_cycles) {
     if (!prof) { mbar_wait(bar, parity); return; }
@@ -378,13 +401,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             mbar_init(ring_empty(s), SUMS ? 8 : 4);      // the four converter warps and the four summer warps of the chunk
         }
         for (int s = 0; s < kTcAStages; ++s) {
-            mbar_init(full_a(s), 128);
+            mbar_init(full_a(s), 4);                     // one arrival per converter warp
             mbar_init(empty_a(s), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(acc_full(i), 1);
-            mbar_init(acc_empty(i), 128);
-            mbar_init(sort_ready(i), 64);
+            mbar_init(acc_empty(i), 4);                  // one arrival per epilogue warp
+            mbar_init(sort_ready(i), 2);                 // one arrival per sorter warp
             mbar_init(sort_free(i), 4 * (NB / 2 < kTcSumGroups ? NB / 2 : kTcSumGroups));   // the summer warps that have chunk pairs
         }
         for (int i = 0; i < kTcTileQ; ++i) mbar_init(tq_full(i), 1);
@@ -489,7 +512,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             tc_st1(tmem_base + lane_base + kApartCol0 + (uint32_t)(par * 8 + blk), __float_as_uint(a));     // read by this pixel's epilogue thread
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(full_a(as));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(as));      // one arrival per warp: 32 times fewer barrier events to wake the waiters
             if (prof) dbg[3] += clock64() - t_cv0;         // centring / splitting / tcgen05.st / wait::st
             blk += kTcConvGroups;
         }
@@ -701,7 +725,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
 #pragma unroll
             for (int b = 0; b < 8; ++b) a_tot += b < NB ? __uint_as_float(av[b]) : 0.f;
             tc_fence_before();
-            mbar_arrive(acc_empty(par));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(par));
             if (PARTIAL) {
                 // this CTA covers one channel slice: park the partial dot products (scaled back by -1/2: B holds -2 Q)
                 // and the partial sum_j w_j x'_j^2 for split_finish_kernel, which adds the slices in order
@@ -749,12 +774,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             int q = 0;
             for (int t = 0; tile_at(t) >= 0; ++t) {
                 const int par = t & 1;
-                if (t >= 2) mbar_wait_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
+                if (t >= 2) mbar_wait_slack_t(acc_empty(par), (((uint32_t)t >> 1) - 1) & 1, 64, prof, dbg[0]);
                 const uint32_t d0 = tmem_base + kAccCol0 + (uint32_t)par * kAccSet, d1 = d0 + 64;
                 for (int b = 0; b < NB; ++b, ++q) {
                     const int as = q & (kTcAStages - 1);
                     const uint32_t use = (uint32_t)q >> 2;
-                    mbar_wait_t(full_a(as), use & 1, prof, dbg[1]);
+                    mbar_wait_slack_t(full_a(as), use & 1, 64, prof, dbg[1]);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_hi = tmem_base + (uint32_t)as * 64, a_lo = a_hi + 32;
@@ -814,7 +839,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 int npx;
                 tile_of(cur, img, pix0, npx);
                 for (int b = 0; b < NB; ++b) {
-                    mbar_wait_t(ring_empty(stage), rphase ^ 1, prof, dbg[0]);
+                    mbar_wait_slack_t(ring_empty(stage), rphase ^ 1, 100, prof, dbg[0]);
                     const uint32_t dst = ring + (uint32_t)stage * kTcStageBytes;
                     const uint32_t bar = ring_full(stage);
                     mbar_arrive_tx(bar, (uint32_t)kTcStageBytes);
@@ -907,7 +932,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 cutcls[c] = who ? val : -1;
             }
             if (t >= 2) {                                                                    // summers are done with tile t-2
-                if (sw == 0) mbar_wait_t(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, prof, dbg[0]);
+                if (sw == 0) mbar_wait_slack_t(sort_free(par), (((uint32_t)t >> 1) - 1) & 1, 200, prof, dbg[0]);
                 named_bar_sync(1, 64);
             }
 #pragma unroll
@@ -930,7 +955,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
                 if (lane < 4) cuts[par * 8 + lane] = lane == 0 ? n_valid : (lane == 1 ? cutcls[1] : (lane == 2 ? cutcls[2] : cutcls[3]));
                 if (lane < C) cnt[lane] += tot;                  // pixel counts per class
             }
-            mbar_arrive(sort_ready(par));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sort_ready(par));
             named_bar_sync(1, 64);                               // wc is reused by the next tile
         }
     }
