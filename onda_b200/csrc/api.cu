@@ -60,6 +60,14 @@ void timing_end(cudaStream_t s) {
     ++g_timed;
 }
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("ONDA_PDL");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    return on;
+}
+
 int current_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
@@ -95,6 +103,8 @@ __global__ void __launch_bounds__(kTableThreads) table_kernel(float* __restrict_
     // world > 0: `sums` of every rank sit in peer-mapped slots; this kernel is also the all-reduce -- handshake,
     // then every use of sums[i] is the rank-ordered sum over the peers (identical on every rank), and the reduced
     // buffer is written to sums_out for the statistics readers.
+    pdl_launch_dependents();      // the next fused pass may be scheduled (its prologue touches no global memory)
+    pdl_wait();                   // the partial combine has completed
     const TableLayout T = table_layout(C, D);
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;
@@ -298,6 +308,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
                                                               const uint32_t* __restrict__ peer_done,
                                                               const uint32_t* __restrict__ peer_epoch, int peer_world) {
     __shared__ double part[8][32];
+    pdl_launch_dependents();      // the EMA/table kernel may be scheduled now; it waits for this grid to complete
+    pdl_wait();                   // the fused pass has completed
     if (peer_done != nullptr && (int)threadIdx.x < peer_world) {     // `out` is peer-visible: its previous contents must have
         const uint32_t want = *peer_epoch - 1u;                      // been read by every rank (one flag per thread: one round trip)
         unsigned spins = 0;
@@ -878,9 +890,9 @@ int onda_pseudolabel_fused_guarded(const float* feat, const float* prior, const 
     }
     const int class_elems = 2 * C * D + C;
     const int blocks = (class_elems + kStatSlots + 31) / 32;
-    reduce_partials_kernel<<<blocks, 256, 0, stream>>>(p.cta_partials, n_cta, sums_floats(C, D), class_elems,
-                                                       want_sums ? 1 : 0, p.stat_partials, n_stat, want_dist ? 1 : 0, sums,
-                                                       peer_done, peer_epoch, peer_world);
+    ONDA_CUDA_TRY(launch_chained(reduce_partials_kernel, dim3(blocks), dim3(256), 0, stream, p.cta_partials, n_cta, sums_floats(C, D),
+                                 class_elems, want_sums ? 1 : 0, p.stat_partials, n_stat, want_dist ? 1 : 0, sums, peer_done,
+                                 peer_epoch, peer_world));
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
@@ -933,8 +945,9 @@ int onda_ema_update_and_table(float* prototypes, float* squared_mean, const floa
     ONDA_REQUIRE(metric == ONDA_METRIC_EUCLIDEAN || metric == ONDA_METRIC_MAHALANOBIS,
                  "onda_ema_update_and_table: unexpected value for attribute distance_metric (%d)", metric);
     if (metric == ONDA_METRIC_MAHALANOBIS) ONDA_REQUIRE(counter, "onda_ema_update_and_table: mahalanobis needs counter");
-    table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
-                                                                                   table, sums, ma_lambda, PeerTable{}, 0, 0, 0u, nullptr, nullptr, g_debug);
+    ONDA_CUDA_TRY(launch_chained(table_kernel, dim3(round_up(D, 32) / 32), dim3(kTableThreads), 0, (cudaStream_t)stream, prototypes,
+                                 squared_mean, counter, C, D, metric, table, sums, ma_lambda, PeerTable{}, 0, 0, 0u, (float*)nullptr,
+                                 (uint32_t*)nullptr, g_debug));
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
@@ -956,8 +969,9 @@ int onda_ema_update_and_table_allreduce(float* prototypes, float* squared_mean, 
     for (int r = 0; r < world; ++r)
         ONDA_REQUIRE(peer_bufs_host[r] && peer_flags_host[r], "onda_ema_update_and_table_allreduce: null peer pointer for rank %d", r);
     const PeerTable peers = make_peer_table(rank, world, peer_bufs_host, peer_flags_host, peer_done_host);
-    table_kernel<<<round_up(D, 32) / 32, kTableThreads, 0, (cudaStream_t)stream>>>(prototypes, squared_mean, counter, C, D, metric,
-                                                                                   table, nullptr, ma_lambda, peers, rank, world, epoch, sums_out, epoch_counter, g_debug);
+    ONDA_CUDA_TRY(launch_chained(table_kernel, dim3(round_up(D, 32) / 32), dim3(kTableThreads), 0, (cudaStream_t)stream, prototypes,
+                                 squared_mean, counter, C, D, metric, table, (const float*)nullptr, ma_lambda, peers, rank, world, epoch,
+                                 sums_out, epoch_counter, g_debug));
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;

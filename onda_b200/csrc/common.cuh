@@ -36,6 +36,33 @@ int cached_sm_count();
         }                                  \
     } while (0)
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// The kernels of a step (fused pass -> partial combine -> EMA/table -> next fused pass) are launched with the
+// programmatic-stream-serialization attribute: a kernel may be SCHEDULED while its predecessor is still running -- once
+// every CTA of the predecessor has executed pdl_launch_dependents() or exited -- and runs its private prologue
+// (shared/tensor memory only) until pdl_wait(), which returns when the predecessor has completed and its writes are
+// visible.  That hides the launch latency of three kernels per step.  Rules kept by every kernel launched this way:
+// nothing before pdl_wait() reads or writes global memory; every CTA executes pdl_wait() (so completion is transitive
+// along the chain).  A kernel whose predecessor does not take part simply starts when that one has finished.
+bool pdl_enabled();      // api.cu: on unless ONDA_PDL=0
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- geometry ----------------------------------------------------------------
 constexpr int kTilePixels = 128;     // pixels per CTA tile (= 4 warps x 32 lanes = 128 TMEM lanes)
 constexpr int kStatSlots = ONDA_NUM_STATS;

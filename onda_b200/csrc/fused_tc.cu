@@ -375,27 +375,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     volatile int* tq = reinterpret_cast<volatile int*>(smem_raw + L.tq);
 
     const TableLayout T = table_layout(C, D);
-    // ---- one-time setup: tables to shared memory, barriers, tensor memory
+    // ---- one-time setup: barriers, tensor memory, zeroed accumulators -- this CTA's own shared / tensor memory only --
+    // then (pdl_wait: the kernel may have been scheduled while its predecessor was still running) the tables
     float* bias_s = reinterpret_cast<float*>(smem_raw + L.bias);
-    if (tid < 32) bias_s[tid] = tid < C ? p.table[T.off_bias + tid] : 0.f;
-    for (int i = tid; i < Dc; i += kTcThreads) {
-        mus[i] = -p.table[T.off_mu + c_base + i];      // negated: the converters centre with a packed add
-        wsm[i] = p.table[T.off_w + c_base + i];
-    }
     if (SUMS) {
         for (int i = tid; i < 2 * (C * Dc + kTcHeadFloats); i += kTcThreads) acc[i] = 0.f;
         if (tid < 32) cnt[tid] = 0;
         if (tid < 16) cuts[16 + tid] = 0;       // landed[] of the summers' watchers
     }
     if (tid == 0) {
-        {   // B operand table of this CTA's channel slice: one bulk asynchronous copy, issued first and off everybody's
-            // critical path -- only the MMA issuer waits for it, before its first MMA
-            mbar_init(btab_bar, 1);
-            fence_barrier_init();
-            const uint32_t bytes = (uint32_t)(2 * T.BR * Dc) * 4u;
-            mbar_arrive_tx(btab_bar, bytes);
-            bulk_g2s_plain(smem_u32(Btab), p.table + T.off_b + (size_t)c_base * 2 * T.BR, bytes, btab_bar);
-        }
+        mbar_init(btab_bar, 1);
         for (int s = 0; s < nstage; ++s) {
             mbar_init(ring_full(s), 1);                  // the producer's expect_tx arrive; the four tensor copies complete the bytes
             mbar_init(ring_empty(s), SUMS ? 8 : 4);      // the four converter warps and the four summer warps of the chunk
@@ -416,6 +405,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_wait();
+    if (tid == 0) {
+        // B operand table of this CTA's channel slice: one bulk asynchronous copy, off everybody's critical path -- only
+        // the MMA issuer waits for it, before its first MMA
+        const uint32_t bytes = (uint32_t)(2 * T.BR * Dc) * 4u;
+        mbar_arrive_tx(btab_bar, bytes);
+        bulk_g2s_plain(smem_u32(Btab), p.table + T.off_b + (size_t)c_base * 2 * T.BR, bytes, btab_bar);
+    }
+    if (tid < 32) bias_s[tid] = tid < C ? p.table[T.off_bias + tid] : 0.f;
+    for (int i = tid; i < Dc; i += kTcThreads) {
+        mus[i] = -p.table[T.off_mu + c_base + i];      // negated: the converters centre with a packed add
+        wsm[i] = p.table[T.off_w + c_base + i];
     }
     tc_fence_before();
     __syncthreads();
@@ -967,6 +969,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
     const long long t_role_end = PROF ? clock64() : 0;
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) pdl_launch_dependents();      // the partial combine may be scheduled; it waits for this grid to complete
     const long long t_sync_end = PROF ? clock64() : 0;
     if (SUMS) {
         float* out = p.cta_partials + (size_t)blockIdx.x * sums_floats(C, D);
@@ -1096,8 +1099,9 @@ static int launch_tc(FusedParams p, int grid, cudaStream_t stream) {
     const int rc = tc_make_maps(p.feat, p.B, p.D, p.HW, &maps);
     if (rc != ONDA_OK) return rc;
     timing_begin(stream);
-    kern<<<dim3((unsigned)grid, (unsigned)(p.D / p.slice_channels)), kTcThreads, smem, stream>>>(p, maps);
+    const cudaError_t le = launch_chained(kern, dim3((unsigned)grid, (unsigned)(p.D / p.slice_channels)), dim3(kTcThreads), smem, stream, p, maps);
     timing_end(stream);
+    ONDA_CUDA_TRY(le);
     ONDA_CUDA_TRY(cudaGetLastError());
     count_launch(1);
     return ONDA_OK;
