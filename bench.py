@@ -463,6 +463,7 @@ def run_onda(args):
         "config": workload_config(d, world, args),
         "launch_mode": "CUDA graph replay (one graph per input set)" if graphs is not None else "eager launches",
         "tile_schedule": args.tile_schedule,
+        "programmatic_dependent_launch": os.environ.get("ONDA_PDL", "1") != "0",
         "input_sets": len(sets),
         "exchange": (None if world == 1 else
                      {"requested": args.allreduce, "effective": h.allreduce,

@@ -458,6 +458,50 @@ def test_step_is_bit_reproducible(B, D, impl):
             assert torch.equal(a, b)
 
 
+_CHAIN_SCRIPT = r"""
+import hashlib, sys, torch
+sys.path.insert(0, {root!r})
+from oracle import proto_oracle as po
+from onda_b200 import prototype_handler
+dev = torch.device("cuda:0")
+case = po.synth_case(91, 6, 256, 65, 129)
+h = prototype_handler(ma_lambda=0.9995, tau=1.0, thresh=0.3, distance_metric="mahalanobis", impl="tcgen05", tile_schedule="fixed")
+h.prototypes, h.squared_mean, h.counter = (case[k].clone().to(dev) for k in ("protos", "sq_mean", "counter"))
+feat, prior, out = (case[k].to(dev) for k in ("feat", "prior", "out"))
+m = hashlib.sha256()
+for step in range(6):                    # back-to-back steps: every kernel of the chain follows its predecessor directly
+    labels, soft = h.pseudo_labels_fused(feat, prior, out)
+    h.ma(feat, out)
+g = torch.cuda.CUDAGraph()               # and the same chain captured and replayed
+with torch.cuda.graph(g):
+    labels, soft = h.pseudo_labels_fused(feat, prior, out)
+    h.ma(feat, out)
+for _ in range(5):
+    g.replay()
+torch.cuda.synchronize()
+for t in (labels, soft, h.prototypes, h.squared_mean):
+    m.update(t.cpu().numpy().tobytes())
+print("HASH", m.hexdigest())
+"""
+
+
+def test_programmatic_launch_chain_changes_no_bit():
+    """The step's kernels are launched with the programmatic-stream-serialization attribute (a kernel may start while its
+    predecessor runs and waits in griddepcontrol.wait before touching global memory).  Eleven chained steps -- six eager,
+    five replays of a captured graph -- must give the same bits as plain launches (ONDA_PDL=0), and the same bits twice."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = _CHAIN_SCRIPT.format(root=root)
+    hashes = []
+    for pdl in ("1", "0", "1"):
+        env = dict(os.environ, ONDA_PDL=pdl)
+        out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        hashes.append([ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][-1])
+    assert hashes[0] == hashes[1] == hashes[2]
+
+
 # --------------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties
 # --------------------------------------------------------------------------------------
