@@ -1,6 +1,7 @@
 // extern "C" entry points of include/onda_b200.h plus the small kernels around the fused pass:
 // distance-table build, fixed-order partial reduction, EMA / cumulative prototype updates and
 // the prior-mix / switch-statistics kernel.
+#include <mutex>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,30 +35,31 @@ void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n
 
 // ---- optional kernel timing (roofline report) ----------------------------------------------
 constexpr int kMaxTimed = 4096;
+static std::mutex g_timing_mu;      // the diagnostics below may be driven from several host threads
 static int g_timing = 0;            // 0 = off, n > 0 = bracket every n-th launch of the dominant kernel
 static int g_timing_seen = 0;
-static bool g_timing_open = false;
 static int g_timed = 0;
 static cudaEvent_t g_ev[kMaxTimed][2];
 static int g_ev_made = 0;
+static thread_local int t_open_slot = -1;      // the event pair this thread's current launch is bracketed by
 
 void timing_begin(cudaStream_t s) {
-    g_timing_open = false;
+    t_open_slot = -1;
+    std::lock_guard<std::mutex> lock(g_timing_mu);
     if (g_timing <= 0 || g_timed >= kMaxTimed) return;
     if ((g_timing_seen++ % g_timing) != 0) return;
-    g_timing_open = true;
     while (g_ev_made <= g_timed) {
         cudaEventCreate(&g_ev[g_ev_made][0]);
         cudaEventCreate(&g_ev[g_ev_made][1]);
         ++g_ev_made;
     }
-    cudaEventRecord(g_ev[g_timed][0], s);
+    t_open_slot = g_timed++;
+    cudaEventRecord(g_ev[t_open_slot][0], s);
 }
 void timing_end(cudaStream_t s) {
-    if (!g_timing_open) return;
-    g_timing_open = false;
-    cudaEventRecord(g_ev[g_timed][1], s);
-    ++g_timed;
+    if (t_open_slot < 0) return;
+    cudaEventRecord(g_ev[t_open_slot][1], s);
+    t_open_slot = -1;
 }
 
 bool pdl_enabled() {
@@ -717,6 +719,7 @@ int onda_debug_set_buffer(void* device_buffer) {
 }
 
 int onda_kernel_timing_enable(int enable) {
+    std::lock_guard<std::mutex> lock(g_timing_mu);
     g_timing = enable > 0 ? enable : 0;
     g_timing_seen = 0;
     g_timed = 0;
@@ -725,6 +728,7 @@ int onda_kernel_timing_enable(int enable) {
 
 int onda_kernel_timing_read(float* total_ms_host, int* launches_host) {
     ONDA_REQUIRE(total_ms_host && launches_host, "onda_kernel_timing_read: null pointer");
+    std::lock_guard<std::mutex> lock(g_timing_mu);
     float total = 0.f;
     for (int i = 0; i < g_timed; ++i) {
         ONDA_CUDA_TRY(cudaEventSynchronize(g_ev[i][1]));

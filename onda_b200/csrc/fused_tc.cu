@@ -828,7 +828,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fused_tc_kernel(const FusedPara
             // fixed round-robin tile blockIdx.x + t * gridDim.x, bit-reproducible.
             const int G = (int)gridDim.x;
             unsigned* counter = p.sched + blockIdx.y;
-            const bool drawing = p.dynamic_tiles != 0 && p.tiles > 2 * G;      // else: tile blockIdx.x + t * gridDim.x, as a fixed schedule
+            // (not for channel slices: the slices of a tile should run at the same time, and measured 0.8 % slower at D = 2048)
+            const bool drawing = p.dynamic_tiles != 0 && p.tiles > 2 * G && gridDim.y == 1;      // else: tile blockIdx.x + t * gridDim.x, as a fixed schedule
             int cur = (int)blockIdx.x, nxt = (int)blockIdx.x + G < p.tiles ? (int)blockIdx.x + G : -1;
             tq[0] = cur;
             tq[1] = nxt;
