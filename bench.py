@@ -112,8 +112,10 @@ class ClockSampler:
                 "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
 
 
-def gpu_inputs(torch, device, d, n_sets, seed, block=8, margin=4.0):
-    """Synthetic Cityscapes-shaped inputs generated on the device (SURVEY.md 8d recipe)."""
+def gpu_inputs(torch, device, d, n_sets, seed, block=8, margin=4.0, shape=None):
+    """Synthetic Cityscapes-shaped inputs generated on the device (SURVEY.md 8d recipe).  ``shape`` = (images, h, w)
+    overrides the bench workload's geometry (the other BASELINE configs)."""
+    B_PER_GPU, H, W = shape if shape is not None else (globals()["B_PER_GPU"], globals()["H"], globals()["W"])
     g = torch.Generator(device=device).manual_seed(seed)
     protos = torch.randn(C, d, generator=g, device=device) * 2.5
     sq_mean = protos ** 2 + torch.rand(C, d, generator=g, device=device) * 1.5 + 0.5
@@ -132,6 +134,62 @@ def gpu_inputs(torch, device, d, n_sets, seed, block=8, margin=4.0):
         prior = (torch.randn(B_PER_GPU, C, H, W, generator=g, device=device) * 3 + 4 * hot).softmax(1)
         sets.append((feat.contiguous(), prior.contiguous(), out.contiguous()))
     return protos, sq_mean, counter, sets
+
+
+def other_config_numbers(torch, device, lib, steps=40):
+    """The other BASELINE configs' prototype path on this GPU, measured like the headline (graph-replayed steps over
+    rotating input sets larger than twice the L2, kernel time from CUDA events in a short eager loop): parity of these
+    shapes is tests/test_gpu_parity.py (test_full_size_oracle_parity, test_oracle_parity_shapes)."""
+    from onda_b200 import prototype_handler
+    from onda_b200 import _native as nat
+    peak, _ = hbm_peak()
+    out = {}
+    for name, (b, d, hh, ww) in (("configs[0] B=1 D=2048 65x129", (1, 2048, 65, 129)),
+                                 ("configs[1] prototype part B=1 D=256 65x129", (1, 256, 65, 129)),
+                                 ("configs[3] B=8 D=256 129x257", (8, 256, 129, 257))):
+        n = b * hh * ww
+        set_bytes = n * algorithmic_bytes_per_pixel(d)
+        n_sets = int(max(2, min(32, -(-2.2 * 126e6 // set_bytes))))
+        protos, sq_mean, counter, sets = gpu_inputs(torch, device, d, n_sets, 4321, shape=(b, hh, ww))
+        h = prototype_handler(**PARAMS)
+        h.prototypes, h.squared_mean, h.counter = protos, sq_mean, counter
+
+        def eager(i):
+            feat, prior, logits = sets[i % n_sets]
+            h.pseudo_labels_fused(feat, prior, logits)
+            h.ma(feat, logits)
+        for i in range(3):
+            eager(i)
+        lib.onda_kernel_timing_enable(1)
+        for i in range(8):
+            eager(i)
+        torch.cuda.synchronize()
+        tot_ms, n_timed = nat.C.c_float(0), nat.C.c_int(0)
+        nat.check(lib.onda_kernel_timing_read(nat.C.byref(tot_ms), nat.C.byref(n_timed)))
+        lib.onda_kernel_timing_enable(0)
+        graphs = []
+        for k in range(n_sets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eager(k)
+            graphs.append(g)
+        for i in range(5):
+            graphs[i % n_sets].replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            graphs[i % n_sets].replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        kernel_ms = tot_ms.value / max(n_timed.value, 1)      # D > 256: the tcgen05 kernel alone (its finishing launch is in the step)
+        out[name] = {"ms_per_step": ms, "px_per_s": n / (ms * 1e-3), "kernel": h.impl, "kernel_ms": kernel_ms,
+                     "roofline_frac_kernel": set_bytes / (kernel_ms * 1e-3) / 1e9 / peak if kernel_ms > 0 else None,
+                     "roofline_frac_step": set_bytes / (ms * 1e-3) / 1e9 / peak, "input_sets": n_sets, "steps": steps}
+        del graphs, sets, h
+        torch.cuda.empty_cache()
+    return out
 
 
 def cpu_reference_rate(torch, d, images, steps, warmup, threads):
@@ -490,6 +548,8 @@ def run_onda(args):
         line["cpu_baseline"] = {"value": px / best, "unit": UNIT, "cores": threads, "kind": kind,
                                 "sample": f"the full batch ({B_PER_GPU} images, {px} px), best of {reps} after 1 warm-up, {what}"}
         line["aux_kernels"] = aux_kernel_numbers(torch, device)
+        if d == 256 and B_PER_GPU == 32 and args.kernel == "auto":      # the default run also reports the other configs
+            line["other_configs"] = other_config_numbers(torch, device, lib)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
