@@ -73,6 +73,13 @@ unsigned long long onda_launch_count(void);
 int onda_kernel_timing_enable(int enable);
 int onda_kernel_timing_read(float* total_ms_host, int* launches_host);
 
+/* Launch chain.  onda_pseudolabel_fused[_guarded] (its tcgen05 kernel and the combine of the per-CTA partials) and
+ * onda_ema_update_and_table[_allreduce] launch their kernels with the programmatic-stream-serialization attribute: on
+ * one stream, a kernel of the chain may be scheduled while its predecessor is still running and waits
+ * (griddepcontrol.wait) before its first global-memory access, so back-to-back steps do not pay the launch latencies.
+ * Results are bit-identical to plain launches; ONDA_PDL=0 in the environment (read once) selects plain launches.
+ * The kernel-timing diagnostics above are thread-safe; the tile schedule and the debug buffer are process-wide settings. */
+
 /* Tile schedule of the tcgen05 kernel (process-wide; returns the previous value).  1 (default, or ONDA_TC_DYNAMIC_TILES
  * unset): tiles beyond the first two per SM are drawn from a device counter -- fastest, but which SM accumulates which
  * tile, and with it the last bits of the class sums, varies from run to run.  0: fixed round-robin schedule, class sums
