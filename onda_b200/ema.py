@@ -42,9 +42,10 @@ def _rows(src, dst, mode):
 
 
 class WeightEma:
-    """The chunk table of a (model, ema_model) pair; ``update(a)`` is one launch."""
+    """The chunk table of a (model, ema_model) pair; ``update(a)`` is one launch.  ``copy_only=True`` makes every row a
+    byte copy: the table of a snapshot (``update_dynamic``)."""
 
-    def __init__(self, model, ema_model):
+    def __init__(self, model, ema_model, copy_only=False):
         self._lib = nat.load()
         params = list(zip(model.parameters(), ema_model.parameters()))
         buffers = list(zip(model.buffers(), ema_model.buffers()))
@@ -52,7 +53,8 @@ class WeightEma:
         self._pairs = params + buffers          # keeps the tensors alive
         rows = []
         for q, k in params:
-            rows += _rows(q.data, k.data, 0)
+            if q.numel():
+                rows += _rows(q.data, k.data, 1 if copy_only else 0)
         for q, k in buffers:
             if q.numel():
                 rows += _rows(q.data, k.data, 1)
@@ -87,3 +89,20 @@ def update_ema(model, ema_model, ema_update):
     if plan is None or not plan.still_valid(model, ema_model):
         plan = _cache[key] = WeightEma(model, ema_model)
     plan.update(ema_update)
+
+
+_snap_cache = {}
+
+
+def update_dynamic(model, dynamic_model):
+    """The copy inside ``online_proDA.update_dynamic`` (prototypes.py:99-102: ``self.dynamic_model = deepcopy(self.model)``,
+    fired by ``evaluate_update_dynamic`` :396-405 when the confidence derivative leaves its band): every parameter and
+    buffer of ``model`` is copied into the EXISTING ``dynamic_model`` in one launch (byte for byte) instead of a module
+    deep copy (allocation plus one copy kernel per tensor).  The caller keeps the reference's follow-up
+    (``models_default_config()``: train/eval modes).  Returns ``dynamic_model``."""
+    key = (id(model), id(dynamic_model))
+    plan = _snap_cache.get(key)
+    if plan is None or not plan.still_valid(model, dynamic_model):
+        plan = _snap_cache[key] = WeightEma(model, dynamic_model, copy_only=True)
+    plan.update(0.0)          # the blend factors are unused by copy rows
+    return dynamic_model

@@ -744,6 +744,17 @@ def test_weight_ema_is_bit_identical_to_the_reference_expression():
     assert all(torch.equal(got.data.cpu(), want) for got, want in zip(k.parameters(), pk))
     with pytest.raises(RuntimeError, match="CUDA"):
         WeightEma(Net(), Net())
+    # update_dynamic (prototypes.py:99-102: dynamic_model = deepcopy(model)): every parameter and buffer copied into the
+    # existing module in one launch, the source untouched; a second call reuses the cached chunk table
+    from onda_b200 import update_dynamic
+    dyn = Net().to(dev())
+    for _ in range(2):
+        assert update_dynamic(q, dyn) is dyn
+        for got, want in zip(list(dyn.parameters()) + list(dyn.buffers()), list(q.parameters()) + list(q.buffers())):
+            assert got.dtype == want.dtype and torch.equal(got.data, want.data) and got.data_ptr() != want.data_ptr()
+        with torch.no_grad():
+            q.w_small.add_(1.0)                                                 # the next snapshot must see the change
+    assert all(torch.equal(got.data.cpu(), want) for got, want in zip(list(q.parameters())[1:2], pq[1:2]))
 
 
 @pytest.mark.parametrize("h,w,H,W", [(9, 17, 65, 129), (10, 13, 37, 50), (33, 65, 257, 513), (6, 7, 6, 7)])
