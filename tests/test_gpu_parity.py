@@ -751,7 +751,8 @@ def test_weight_ema_is_bit_identical_to_the_reference_expression():
     for _ in range(2):
         assert update_dynamic(q, dyn) is dyn
         for got, want in zip(list(dyn.parameters()) + list(dyn.buffers()), list(q.parameters()) + list(q.buffers())):
-            assert got.dtype == want.dtype and torch.equal(got.data, want.data) and got.data_ptr() != want.data_ptr()
+            assert got.dtype == want.dtype and torch.equal(got.data, want.data)
+            assert got.numel() == 0 or got.data_ptr() != want.data_ptr()
         with torch.no_grad():
             q.w_small.add_(1.0)                                                 # the next snapshot must see the change
     assert all(torch.equal(got.data.cpu(), want) for got, want in zip(list(q.parameters())[1:2], pq[1:2]))
