@@ -77,6 +77,10 @@ __device__ __forceinline__ void load_pixel_row_at(const float* lp, int C, unsign
     for (int k = 0; k < CP; ++k) v[k] = (k < C) ? __ldg(lp + (unsigned)k * hw) : 0.f;
 }
 
+// NaN-propagating min / max (one FMNMX each): what `(a < b || a != a) ? a : b` spells with two compares and a select
+__device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
 // First maximal index with torch semantics (prototype_handler.onehot, prototype_handler.py:83-86).
 template <int CP>
 __device__ __forceinline__ int first_argmax(const float (&v)[CP], int C) {
@@ -88,20 +92,21 @@ __device__ __forceinline__ int first_argmax(const float (&v)[CP], int C) {
     return arg;
 }
 
-// Same result, cheaper in the common case: plain greater-than scan, and only a row that contains a NaN takes the
-// full torch rule (first NaN wins).
+// Same result, cheaper in the common case: a NaN-propagating maximum (one FMNMX per class), then the first index that
+// holds it (scanned downwards: a compare and a select per class); only a row that contains a NaN takes the full torch
+// rule (first NaN wins).  -0 == +0 like torch's `>` scan: the first of them wins.
 template <int CP>
 __device__ __forceinline__ int first_argmax_fast(const float (&v)[CP], int C) {
     float best = v[0];
-    int arg = 0;
-    bool has_nan = v[0] != v[0];
 #pragma unroll
     for (int k = 1; k < CP; ++k)
-        if (k < C) {
-            has_nan |= v[k] != v[k];
-            if (v[k] > best) { best = v[k]; arg = k; }
-        }
-    return has_nan ? first_argmax<CP>(v, C) : arg;
+        if (k < C) best = fmax_nan(best, v[k]);
+    if (best != best) return first_argmax<CP>(v, C);
+    int arg = 0;
+#pragma unroll
+    for (int k = CP - 1; k >= 1; --k)
+        if (k < C) arg = (v[k] == best) ? k : arg;
+    return (v[0] == best) ? 0 : arg;
 }
 
 // ---- fast single-instruction math (MUFU, flush-to-zero forms: no denormal fix-up code): relative error ~2^-22,
@@ -109,9 +114,6 @@ __device__ __forceinline__ int first_argmax_fast(const float (&v)[CP], int C) {
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-// NaN-propagating min / max (one FMNMX each): what `(a < b || a != a) ? a : b` spells with two compares and a select
-__device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // Everything after the squared distances for one pixel (one thread).  Follows
@@ -191,15 +193,27 @@ __device__ __forceinline__ void rectify_pixel(float (&v)[CP], const float (&pri)
     label = (best < thresh) ? ONDA_IGNORE_LABEL : arg;
 }
 
-// Copies `rows` staged rows of C floats (row stride CP+1 in shared memory) to a pixel-major
-// global array with fully coalesced 128-byte stores.  One warp, its own 32 rows.
+// Copies `rows` staged rows of C floats (row stride S in shared memory) to a pixel-major global array with fully
+// coalesced 128-byte stores.  One warp, its own 32 rows.  S is the smallest ODD number >= C (conflict-free staging
+// writes); for an odd class count (19 in every OnDA config) the staged rows are therefore contiguous and the copy is
+// flat: one load and one store per 32 floats, no index arithmetic.
 template <int CP>
-__device__ __forceinline__ void warp_copy_rows(const float* stage_rows, float* gdst, int rows, int C, int lane) {
+__device__ __forceinline__ void warp_copy_rows(const float* stage_rows, float* gdst, int rows, int C, int S, int lane) {
     const int total = rows * C;
+    if (S == C) {
+        if (rows == 32) {
+#pragma unroll
+            for (int i = 0; i < CP; ++i)
+                if (i < C) gdst[lane + 32 * i] = stage_rows[lane + 32 * i];
+        } else {
+            for (int e = lane; e < total; e += 32) gdst[e] = stage_rows[e];
+        }
+        return;
+    }
     const int dr = 32 / C, dk = 32 % C;  // element e -> (row, k) advanced incrementally: no division per store
     int row = lane / C, k = lane % C;
     for (int e = lane; e < total; e += 32) {
-        gdst[e] = stage_rows[row * (CP + 1) + k];
+        gdst[e] = stage_rows[row * S + k];
         k += dk;
         row += dr;
         if (k >= C) { k -= C; row += 1; }
@@ -207,7 +221,7 @@ __device__ __forceinline__ void warp_copy_rows(const float* stage_rows, float* g
 }
 
 // Tail for one tile row handled by thread `t` (pixel n = tile_base + t).  `stage` is a
-// [128][CP+1] shared-memory slab; rows 32*warp .. 32*warp+31 belong to this warp.
+// [128][CP+1] shared-memory slab (rows are staged at the odd stride C | 1 <= CP + 1); rows 32*warp .. 32*warp+31 belong to this warp.
 // `tile_rows` = number of valid rows of this tile (rows tile_base .. tile_base + tile_rows - 1 exist).
 template <int CP, bool WANT_DIST>
 __device__ __forceinline__ void finish_pixel_rows(const FusedParams& p, const int C, float (&d2)[CP], long long tile_base,
@@ -247,22 +261,23 @@ __device__ __forceinline__ void finish_pixel_rows(const FusedParams& p, const in
     const long long warp_base = tile_base + 32 * warp;
     const int remain = tile_rows - 32 * warp;
     const int rows = remain <= 0 ? 0 : (remain < 32 ? remain : 32);
-    float* my_rows = stage + (32 * warp) * (CP + 1);
+    const int S = C | 1;                                  // row stride of the staged rows: odd, <= CP + 1
+    float* my_rows = stage + (32 * warp) * S;
     if (p.soft != nullptr) {
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CP; ++k)
-            if (k < C) stage[t * (CP + 1) + k] = d2[k];
+            if (k < C) stage[t * S + k] = d2[k];
         __syncwarp();
-        warp_copy_rows<CP>(my_rows, p.soft + warp_base * C, rows, C, lane);
+        warp_copy_rows<CP>(my_rows, p.soft + warp_base * C, rows, C, S, lane);
     }
     if (WANT_DIST && p.dist != nullptr) {
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < CP; ++k)
-            if (k < C) stage[t * (CP + 1) + k] = dsh[k];
+            if (k < C) stage[t * S + k] = dsh[k];
         __syncwarp();
-        warp_copy_rows<CP>(my_rows, p.dist + warp_base * C, rows, C, lane);
+        warp_copy_rows<CP>(my_rows, p.dist + warp_base * C, rows, C, S, lane);
     }
 }
 
