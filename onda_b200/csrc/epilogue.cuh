@@ -130,13 +130,24 @@ __device__ __forceinline__ void rectify_pixel(float (&v)[CP], const float (&pri)
                                               float& m_out, float& maxq, float& maxprior, float& entropy) {
     const float inf = __int_as_float(0x7f800000);
     float dmin = inf, dmax = 0.f;
+    if (inv_tau > 0.f) {                                         // the usual case: the row maximum is not needed
 #pragma unroll
-    for (int k = 0; k < CP; ++k) {
-        if (k < C) {
-            const float d = fast_sqrt(fmax_nan(v[k], 0.f));      // rounding can make a ~0 squared distance negative; keeps NaN
-            v[k] = d;
-            dmin = fmin_nan(d, dmin);                            // a NaN distance makes the whole row NaN, like torch.min
-            dmax = fmaxf(dmax, d);
+        for (int k = 0; k < CP; ++k) {
+            if (k < C) {
+                const float d = fast_sqrt(fmax_nan(v[k], 0.f));  // rounding can make a ~0 squared distance negative; keeps NaN
+                v[k] = d;
+                dmin = fmin_nan(d, dmin);                        // a NaN distance makes the whole row NaN, like torch.min
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CP; ++k) {
+            if (k < C) {
+                const float d = fast_sqrt(fmax_nan(v[k], 0.f));
+                v[k] = d;
+                dmin = fmin_nan(d, dmin);
+                dmax = fmaxf(dmax, d);
+            }
         }
     }
     // softmax(-d'/tau) = 2^((d' - ref) * scale) / sum, ref = the d' whose exponent is the row maximum:
@@ -144,15 +155,30 @@ __device__ __forceinline__ void rectify_pixel(float (&v)[CP], const float (&pri)
     const float scale = -1.4426950408889634f * inv_tau;
     const float ref = inv_tau > 0.f ? 0.f : dmax - dmin;
     float esum = 0.f, emax = 0.f;
+    if (WANT_DIST) {
 #pragma unroll
-    for (int k = 0; k < CP; ++k) {
-        if (k < C) {
-            const float ds = v[k] - dmin;
-            if (WANT_DIST) dsh[k] = ds;
-            const float e = fast_ex2((ds - ref) * scale);
-            v[k] = e;
-            esum += e;
-            emax = fmaxf(emax, e);
+        for (int k = 0; k < CP; ++k) {
+            if (k < C) {
+                const float ds = v[k] - dmin;
+                dsh[k] = ds;
+                const float e = fast_ex2((ds - ref) * scale);
+                v[k] = e;
+                esum += e;
+                emax = fmaxf(emax, e);
+            }
+        }
+    } else {
+        // (d - dmin - ref) * scale as one fused multiply-add per class: the rounding of the row constant c0 is a factor
+        // common to the whole row, which the normalisation by the row sum removes again
+        const float c0 = -(dmin + ref) * scale;
+#pragma unroll
+        for (int k = 0; k < CP; ++k) {
+            if (k < C) {
+                const float e = fast_ex2(fmaf(v[k], scale, c0));
+                v[k] = e;
+                esum += e;
+                emax = fmaxf(emax, e);
+            }
         }
     }
     const float inv_e = fast_rcp(esum);
