@@ -124,6 +124,25 @@ def tweak_edge(case):
     prior[0, 6, 1, 0] = 1.0
 
 
+def nan_rows_case():
+    """Rows where the reference's arithmetic degenerates (prototype_handler.py:159-166): a prior that is zero for every
+    class (0 / 0 -> NaN row, torch.max gives (NaN, 0), `NaN < thresh` is False -> label 0), a NaN feature vector (NaN
+    distances -> NaN row), and a negative tau (the softmax prefers the FARTHEST prototype).  Stored under a name the
+    ops_* globs do not match: the CPU oracle is pinned to it; the CUDA path is compared with the oracle on such rows in
+    tests/test_gpu_parity.py::test_zero_rectified_row_keeps_label_zero_like_the_reference."""
+    out = {}
+    for tag, tau in (("pos", 1.0), ("neg", -0.8)):
+        case = synth_case(61, 1, 32, 4, 5)
+        case["prior"][0, :, 1, 2] = 0.0
+        case["feat"][0, :, 2, 3] = float("nan")
+        hd = make_handler("mahalanobis", case, 0.9995, tau, 0.3)
+        labels = hd.pseudo_labels(case["feat"], case["prior"])
+        soft = hd.pseudo_labels(case["feat"], case["prior"], soft=True)
+        out.update({f"ref_labels_{tag}": labels, f"ref_soft_{tag}": soft})
+    npz("edge_nan_rows.npz", feat=case["feat"], prior=case["prior"], protos=case["protos"], sq_mean=case["sq_mean"],
+        counter=case["counter"], **out)
+
+
 def append_case():
     g = torch.Generator().manual_seed(77)
     hd = prototype_handler(distance_metric="mahalanobis")
@@ -503,6 +522,7 @@ def main():
     ops_case("ops_mahal_d256_legacy.npz", 16, 1, 256, 17, 21, "mahalanobis", protos=p_legacy, counter=c_legacy)
     ops_case("ops_mahal_d2048.npz", 17, 1, 2048, 9, 10, "mahalanobis")
     append_case()
+    nan_rows_case()
     monitor_trace()
     sequence_case()
     stats_case()

@@ -630,6 +630,26 @@ def test_zero_rectified_row_keeps_label_zero_like_the_reference():
     assert float((soft.cpu()[ok] - ref_soft[ok]).abs().max()) <= 1e-5
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+def test_degenerate_rows_golden(impl):
+    """golden/edge_nan_rows.npz (outputs of the real reference): a zero prior row, a NaN feature vector, and a negative
+    tau.  NaN rows in the same places with label 0, labels equal off near-ties, the rest within 1e-5."""
+    z = np.load(os.path.join(GOLDEN, "edge_nan_rows.npz"))
+    need_shape(impl, z["protos"].shape[1])
+    for tag, tau in (("pos", 1.0), ("neg", -0.8)):
+        h = make_handler(T(z["protos"]), T(z["sq_mean"]), T(z["counter"]), "mahalanobis", tau=tau, impl=impl)
+        feat, prior = T(z["feat"]).to(dev()), T(z["prior"]).to(dev())
+        labels = h.pseudo_labels(feat, prior).cpu()
+        soft = h.pseudo_labels(feat, prior, soft=True).cpu()
+        ref_labels, ref_soft = T(z[f"ref_labels_{tag}"]), T(z[f"ref_soft_{tag}"])
+        nan_rows = torch.isnan(ref_soft).all(dim=1)
+        assert torch.equal(torch.isnan(soft).all(dim=1), nan_rows) and int(nan_rows.sum()) == 2
+        assert bool((labels.flatten()[nan_rows] == 0).all())
+        ok = ~nan_rows
+        assert float((soft[ok] - ref_soft[ok]).abs().max()) <= 1e-5
+        check_labels(labels[ok], ref_labels[ok], ref_soft[ok], 0.3)
+
+
 LABEL_MAPS = ["one_class", "two_classes_odd_split", "aligned_runs_of_32", "stripes_of_5", "random", "ragged_tail"]
 
 

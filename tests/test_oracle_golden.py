@@ -124,6 +124,23 @@ def test_switch_statistics_and_entropy():
     np.testing.assert_allclose(po.normalised_entropy(la.softmax(1)).numpy(), z["ref_entropy"], atol=1e-7)
 
 
+def test_degenerate_rows_match_reference():
+    """Zero prior row (0 / 0), NaN feature vector, negative tau: the restatement gives what the real reference gave
+    (labels bit-exact, NaN rows in the same places, the rest within 1e-7) -- golden/edge_nan_rows.npz."""
+    z = np.load(os.path.join(GOLDEN, "edge_nan_rows.npz"))
+    for tag, tau in (("pos", 1.0), ("neg", -0.8)):
+        h = po.OracleHandler(ma_lambda=0.9995, tau=tau, thresh=0.3, distance_metric="mahalanobis")
+        h.prototypes, h.squared_mean, h.counter = T(z["protos"]).clone(), T(z["sq_mean"]).clone(), T(z["counter"]).clone()
+        labels = h.pseudo_labels(T(z["feat"]), T(z["prior"]))
+        soft = h.pseudo_labels(T(z["feat"]), T(z["prior"]), soft=True)
+        assert torch.equal(labels, T(z[f"ref_labels_{tag}"]))
+        ref = z[f"ref_soft_{tag}"]
+        assert np.array_equal(np.isnan(soft.numpy()), np.isnan(ref))
+        assert sorted(np.isnan(ref).all(axis=1).nonzero()[0].tolist()) == [7, 13]
+        assert labels[7].item() == 0 and labels[13].item() == 0
+        np.testing.assert_allclose(np.nan_to_num(soft.numpy()), np.nan_to_num(ref), rtol=0, atol=1e-7)
+
+
 def test_bad_metric_raises():
     with pytest.raises(ValueError):
         po.OracleHandler(distance_metric="cosine")
