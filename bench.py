@@ -21,7 +21,9 @@ HBM; ``e2e`` = the same through the public API from pinned HOST buffers (H2D of 
 and D2H of labels + soft predictions + statistics inside the timed region); ``roofline`` for the
 dominant kernel (algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json); ``cpu_baseline``
 = the reference's own prototype_handler (oracle/_ref, staged by ``__graft_entry__.build()``; the
-oracle port if that file is absent) timed on this box's host cores on the same batch.
+oracle port if that file is absent) timed on this box's host cores on the same batch.  The default single-GPU run
+also reports ``other_configs``: the prototype path of BASELINE configs[0], [1] and [3] measured the same way, and
+``aux_kernels`` (model-weight EMA, evaluation counters).
 """
 from __future__ import annotations
 
